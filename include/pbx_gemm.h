@@ -1,0 +1,184 @@
+/*
+ * pbx_gemm.h -- C-ABI of the B200-native GEMM path (libpbx_gemm.so).
+ *
+ * This is the drop-in boundary.  It replaces the SYCL launcher seam of the
+ * reference,
+ *     Gemm_Launcher<...>::_select_gemm(sb_handle, M, N, K, alpha, a_, lda,
+ *                                      stridea, b_, ldb, strideb, beta, C,
+ *                                      ldc, stridec, batch_size, deps)
+ *     (reference include/interface/gemm_launcher.h:37-52,
+ *      src/interface/gemm_launcher.hpp:39-64)
+ * together with everything below it (backend heuristics
+ * src/interface/blas3/backend/nvidia_gpu.hpp:40-260, the Gemm<> kernels in
+ * src/operations/blas3/, SB_Handle::execute(Gemm) in
+ * src/sb_handle/portblas_handle.hpp:277-403 and the alpha==0 scal path
+ * src/interface/blas1_interface.hpp:438-510).
+ *
+ * Conventions (identical to the reference's interface, README.md:282-289):
+ *   - column-major storage only; dimensions are post-transpose (op(A) is MxK,
+ *     op(B) is KxN, C is MxN); ld >= stored rows.
+ *   - trans chars are case-insensitive 'n' / 't' / 'c' ('c' == 't' for the real
+ *     types handled here, src/interface/gemm_interface.hpp:141-151).
+ *   - alpha/beta live on the HOST.  They are passed by pointer to a host value
+ *     of the *scalar type* listed per entry point.
+ *   - A, B, C are DEVICE pointers owned by the caller (cudaMalloc / torch
+ *     allocations; the reference accepts only device USM, README.md:186-187).
+ *   - batch_type: 0 = strided, 1 = interleaved
+ *     (blas::gemm_batch_type_t, include/operations/blas3_trees.h:59).
+ *   - every call is asynchronous on the handle's CUDA stream.
+ *
+ * Plain pointers and sizes only: no torch / C++ types cross this boundary.
+ * There is no CPU fallback behind these symbols.
+ */
+#ifndef PBX_GEMM_H
+#define PBX_GEMM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBX_VERSION 100
+
+/* ---- status codes ------------------------------------------------------ */
+typedef enum pbx_status {
+  PBX_OK = 0,
+  PBX_ERR_INVALID_TRANSA = 1, /* reference throws invalid_argument("invalid _TransA") gemm_interface.hpp:144 */
+  PBX_ERR_INVALID_TRANSB = 2, /* "invalid _TransB"  gemm_interface.hpp:146 */
+  PBX_ERR_INVALID_STRIDEC = 3, /* "invalid _stridec" gemm_interface.hpp:159 */
+  PBX_ERR_INVALID_STRIDEA = 4, /* "invalid _stridea" gemm_interface.hpp:161 */
+  PBX_ERR_INVALID_STRIDEB = 5, /* "invalid _strideb" gemm_interface.hpp:163 */
+  PBX_ERR_INVALID_ARG = 6,     /* null handle, unknown dtype/batch_type, negative dims */
+  PBX_ERR_CUDA = 7,            /* a CUDA runtime / driver call failed; see pbx_last_error() */
+  PBX_ERR_NO_DEVICE = 8,       /* no sm_100 device: this library has no fallback */
+  PBX_ERR_WORKSPACE = 9        /* split-K workspace could not be allocated */
+} pbx_status_t;
+
+/* ---- element types (in -> out) ----------------------------------------- *
+ * Mirrors the (DATA_TYPE_IN, DATA_TYPE_OUT) matrix the reference instantiates
+ * (src/interface/blas3/gemm.cpp.in:33-137) plus bf16 storage (BASELINE cfg 4). */
+typedef enum pbx_dtype {
+  PBX_F32 = 0,      /* float  -> float   scalar: float   (3xTF32 on tcgen05, fp32 accumulate) */
+  PBX_F64 = 1,      /* double -> double  scalar: double  (DMMA mma.sync f64) */
+  PBX_F16 = 2,      /* half   -> half    scalar: float   (tcgen05 kind::f16, fp32 accumulate) */
+  PBX_F16_F32 = 3,  /* half   -> float   scalar: float   (mixed, gemm.cpp.in:36-39) */
+  PBX_BF16 = 4,     /* bf16   -> bf16    scalar: float   (tcgen05 kind::f16) */
+  PBX_BF16_F32 = 5  /* bf16   -> float   scalar: float */
+} pbx_dtype_t;
+
+/* ---- kernel families (for pbx_set_forced_kernel / pbx_last_kernel) ------ */
+typedef enum pbx_kernel {
+  PBX_KERNEL_AUTO = 0,
+  PBX_KERNEL_SIMT = 1,        /* shared-memory tiled CUDA-core kernel: any alignment, any ld */
+  PBX_KERNEL_TCGEN05 = 2,     /* TMA + tcgen05/TMEM (f16/bf16 direct, f32 as 3xTF32) */
+  PBX_KERNEL_DMMA = 3,        /* fp64 tensor path (mma.sync m8n8k4 f64) */
+  PBX_KERNEL_INTERLEAVED = 4, /* interleaved-batch kernel */
+  PBX_KERNEL_SCAL = 5,        /* alpha == 0 : C = beta*C */
+  PBX_KERNEL_NONE = 6         /* nothing launched (m==0 || n==0 || batch==0, or beta==1 scal) */
+} pbx_kernel_t;
+
+typedef struct pbx_handle_s* pbx_handle_t;
+
+/* ---- handle ------------------------------------------------------------- *
+ * Replaces blas::SB_Handle's device-facing half
+ * (include/sb_handle/portblas_handle.h:46-200): one handle == one device +
+ * one stream, caches the SM count (get_num_compute_units) and owns the
+ * split-K workspace pool (Temp_Mem_Pool, include/sb_handle/temp_memory_pool.h:33-114).
+ * Not thread-safe, like the reference (one handle per thread).              */
+int pbx_create(pbx_handle_t* out, int device_ordinal, void* cuda_stream /* cudaStream_t or NULL */);
+int pbx_destroy(pbx_handle_t h);
+int pbx_set_stream(pbx_handle_t h, void* cuda_stream);
+void* pbx_get_stream(pbx_handle_t h);
+int pbx_get_num_compute_units(pbx_handle_t h);     /* SM count (148 on B200) */
+int pbx_get_device(pbx_handle_t h);
+int pbx_synchronize(pbx_handle_t h);               /* SB_Handle::wait() */
+const char* pbx_last_error(pbx_handle_t h);        /* text of the last failure (may be "") */
+const char* pbx_status_string(int status);         /* the reference's exception text for a status */
+
+/* Testing / tuning hooks. */
+int pbx_set_forced_kernel(pbx_handle_t h, int kernel /* pbx_kernel_t */);
+int pbx_set_split_k(pbx_handle_t h, int slices /* 0 = auto, 1 = never, >1 = force */);
+int pbx_last_kernel(pbx_handle_t h);               /* pbx_kernel_t used by the last call */
+int pbx_last_split_k(pbx_handle_t h);              /* K slices used by the last call */
+int64_t pbx_launch_count(pbx_handle_t h);          /* kernels launched through this handle so far */
+int64_t pbx_workspace_bytes(pbx_handle_t h);       /* current size of the pooled workspace */
+
+/* ---- the GEMM entry point ------------------------------------------------
+ *  C_b <- alpha * op(A_b) * op(B_b) + beta * C_b      b = 0 .. batch-1
+ *
+ *  strided     : X_b = X + b*strideX (elements); strideA/strideB may be 0
+ *                (broadcast); for batch > 1 strideC >= ldc*N is required.
+ *  interleaved : element (r, c, b) lives at X[(c*ldX + r)*batch + b]
+ *                (reference src/operations/blas3/gemm_interleaved.hpp:265-271);
+ *                strides are ignored.
+ *
+ *  Front-end rules restated from src/interface/gemm_interface.hpp:105-185:
+ *   - alpha == 0 is tested FIRST (before trans validation): C <- beta*C over
+ *     the MxN window(s); beta == 1 is a no-op, beta == 0 stores exact zeros.
+ *   - beta == 0 never reads C (NaN-safe, gemm_interface.hpp:85-100).
+ *   - m == 0 || n == 0 || batch == 0: nothing happens; k == 0: C <- beta*C.
+ *  Returns a pbx_status_t.                                                    */
+int pbx_gemm(pbx_handle_t h, int dtype /* pbx_dtype_t */, char transa, char transb,
+             int64_t m, int64_t n, int64_t k,
+             const void* alpha,
+             const void* A, int64_t lda, int64_t stridea,
+             const void* B, int64_t ldb, int64_t strideb,
+             const void* beta,
+             void* C, int64_t ldc, int64_t stridec,
+             int64_t batch, int batch_type);
+
+/* Per-type spellings (what a per-dtype explicit instantiation of
+ * blas::internal::_gemm / _gemm_batched / _gemm_strided_batched binds to). */
+int pbx_sgemm(pbx_handle_t h, char transa, char transb, int64_t m, int64_t n, int64_t k,
+              const float* alpha, const float* A, int64_t lda, int64_t stridea,
+              const float* B, int64_t ldb, int64_t strideb, const float* beta,
+              float* C, int64_t ldc, int64_t stridec, int64_t batch, int batch_type);
+int pbx_dgemm(pbx_handle_t h, char transa, char transb, int64_t m, int64_t n, int64_t k,
+              const double* alpha, const double* A, int64_t lda, int64_t stridea,
+              const double* B, int64_t ldb, int64_t strideb, const double* beta,
+              double* C, int64_t ldc, int64_t stridec, int64_t batch, int batch_type);
+int pbx_hgemm(pbx_handle_t h, char transa, char transb, int64_t m, int64_t n, int64_t k,
+              const float* alpha, const void* A, int64_t lda, int64_t stridea,
+              const void* B, int64_t ldb, int64_t strideb, const float* beta,
+              void* C, int64_t ldc, int64_t stridec, int64_t batch, int batch_type);
+int pbx_hsgemm(pbx_handle_t h, char transa, char transb, int64_t m, int64_t n, int64_t k,
+               const float* alpha, const void* A, int64_t lda, int64_t stridea,
+               const void* B, int64_t ldb, int64_t strideb, const float* beta,
+               float* C, int64_t ldc, int64_t stridec, int64_t batch, int batch_type);
+int pbx_bf16gemm(pbx_handle_t h, char transa, char transb, int64_t m, int64_t n, int64_t k,
+                 const float* alpha, const void* A, int64_t lda, int64_t stridea,
+                 const void* B, int64_t ldb, int64_t strideb, const float* beta,
+                 void* C, int64_t ldc, int64_t stridec, int64_t batch, int batch_type);
+
+/* C <- beta*C on an MxN column-major window (x batch, strided).  Replaces
+ * blas::internal::_scal_matrix (src/interface/blas1_interface.hpp:468-510).
+ * beta == 1: no launch.  beta == 0: stores zeros without reading C.          */
+int pbx_scal_matrix(pbx_handle_t h, int dtype, int64_t m, int64_t n, const void* beta,
+                    void* C, int64_t ldc, int64_t stridec, int64_t batch);
+
+/* ---- host-buffer convenience path (used for the end-to-end metric) -------
+ * Same semantics as pbx_gemm, but A, B, C are HOST pointers (ideally pinned):
+ * stages H2D on the handle's stream, runs the GEMM, copies C back and
+ * synchronises.  Device staging buffers are cached in the handle.
+ * This is what blas::helper::copy_to_device + _gemm + copy_to_host amount to
+ * (reference include/portblas_helper.h:139-191, samples/gemm.cpp:50-63).      */
+int pbx_gemm_host(pbx_handle_t h, int dtype, char transa, char transb,
+                  int64_t m, int64_t n, int64_t k, const void* alpha,
+                  const void* A_host, int64_t lda, int64_t stridea,
+                  const void* B_host, int64_t ldb, int64_t strideb,
+                  const void* beta, void* C_host, int64_t ldc, int64_t stridec,
+                  int64_t batch, int batch_type);
+
+/* ---- device memory helpers (blas::helper::allocate / copy_to_device / ...,
+ * include/portblas_helper.h:54-81,139-219) -------------------------------- */
+int pbx_malloc(pbx_handle_t h, void** dptr, int64_t bytes);
+int pbx_free(pbx_handle_t h, void* dptr);
+int pbx_copy_to_device(pbx_handle_t h, const void* host_src, void* dev_dst, int64_t bytes);
+int pbx_copy_to_host(pbx_handle_t h, const void* dev_src, void* host_dst, int64_t bytes);
+int pbx_fill_bytes(pbx_handle_t h, void* dev_dst, int value, int64_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBX_GEMM_H */

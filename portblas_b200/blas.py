@@ -1,0 +1,187 @@
+"""Host-side mirror of the reference's GEMM interface, in Python, over the C-ABI.
+
+Names, argument order, argument meaning and error behaviour follow the reference:
+
+  blas::SB_Handle                    include/sb_handle/portblas_handle.h:46-200
+  blas::gemm_batch_type_t            include/operations/blas3_trees.h:59
+  blas::_gemm                        include/interface/blas3_interface.h:88-95
+  blas::_gemm_batched                include/interface/blas3_interface.h:99-109
+  blas::_gemm_strided_batched        include/interface/blas3_interface.h:113-123
+
+so that tests/ read like test/unittest/blas3/*gemm*.  (The C++ mirror of the same interface lives
+in include/portblas.hpp; both funnel into the same extern "C" entry points.)
+
+Containers are 1-D torch CUDA tensors -- the analogue of the reference's USM pointers /
+BufferIterator (``buf[offset:]`` plays the role of ``buffer + offset``).  std::invalid_argument
+maps to ValueError with the reference's exact message.  Calls are asynchronous on the handle's
+stream, as in the reference; ``SB_Handle.wait()`` synchronises.
+"""
+from __future__ import annotations
+
+import ctypes
+import enum
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+class gemm_batch_type_t(enum.IntEnum):
+    strided = 0
+    interleaved = 1
+
+
+class PbxError(RuntimeError):
+    pass
+
+
+def _check(h: "SB_Handle", status: int) -> None:
+    if status == _lib.OK:
+        return
+    lib = _lib.load()
+    text = lib.pbx_status_string(status).decode()
+    if 1 <= status <= 5:
+        raise ValueError(text)  # reference: std::invalid_argument(text), gemm_interface.hpp:144-165
+    detail = lib.pbx_last_error(h._h).decode() if h is not None and h._h else ""
+    raise PbxError(f"{text}: {detail}" if detail else text)
+
+
+class SB_Handle:
+    """One device + one stream (reference: one sycl::queue)."""
+
+    def __init__(self, device: int = 0, stream: Optional[object] = None):
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        if stream is None:
+            sptr = torch.cuda.current_stream(device).cuda_stream if torch.cuda.is_available() else 0
+        elif isinstance(stream, int):
+            sptr = stream
+        else:
+            sptr = stream.cuda_stream
+        st = self._lib.pbx_create(ctypes.byref(self._h), int(device), ctypes.c_void_p(sptr))
+        if st != _lib.OK:
+            self._h = None
+            raise PbxError(self._lib.pbx_status_string(st).decode())
+        self.device = int(device)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.pbx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- reference surface -------------------------------------------------------------------
+    def wait(self) -> None:
+        _check(self, self._lib.pbx_synchronize(self._h))
+
+    def get_num_compute_units(self) -> int:
+        return self._lib.pbx_get_num_compute_units(self._h)
+
+    def set_stream(self, stream) -> None:
+        sptr = stream if isinstance(stream, int) else stream.cuda_stream
+        _check(self, self._lib.pbx_set_stream(self._h, ctypes.c_void_p(sptr)))
+
+    # -- testing / tuning hooks -----------------------------------------------------------------
+    def set_forced_kernel(self, kernel: int) -> None:
+        _check(self, self._lib.pbx_set_forced_kernel(self._h, int(kernel)))
+
+    def set_split_k(self, slices: int) -> None:
+        _check(self, self._lib.pbx_set_split_k(self._h, int(slices)))
+
+    @property
+    def last_kernel(self) -> str:
+        return _lib.KERNEL_NAMES[self._lib.pbx_last_kernel(self._h)]
+
+    @property
+    def last_split_k(self) -> int:
+        return self._lib.pbx_last_split_k(self._h)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.pbx_launch_count(self._h))
+
+
+_DTYPES = {
+    (torch.float32, torch.float32): _lib.F32,
+    (torch.float64, torch.float64): _lib.F64,
+    (torch.float16, torch.float16): _lib.F16,
+    (torch.float16, torch.float32): _lib.F16_F32,
+    (torch.bfloat16, torch.bfloat16): _lib.BF16,
+    (torch.bfloat16, torch.float32): _lib.BF16_F32,
+}
+
+
+def _dtype_of(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor) -> int:
+    if a.dtype != b.dtype:
+        raise TypeError("A and B must have the same element type")
+    try:
+        return _DTYPES[(a.dtype, c.dtype)]
+    except KeyError:
+        raise TypeError(f"unsupported (in, out) element types {a.dtype}, {c.dtype}") from None
+
+
+def _scalar(dtype: int, v: float):
+    return ctypes.c_double(v) if dtype == _lib.F64 else ctypes.c_float(v)
+
+
+def _gemm_backend(sb_handle: SB_Handle, transa: str, transb: str, m: int, n: int, k: int, alpha, a, lda,
+                  stridea, b, ldb, strideb, beta, c, ldc, stridec, batch_size, batch_type) -> None:
+    for t in (a, b, c):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.is_contiguous()):
+            raise TypeError("containers must be contiguous CUDA tensors (device USM analogue)")
+    dt = _dtype_of(a, b, c)
+    al, be = _scalar(dt, float(alpha)), _scalar(dt, float(beta))
+    st = sb_handle._lib.pbx_gemm(
+        sb_handle._h, dt, str(transa).encode()[:1], str(transb).encode()[:1], int(m), int(n), int(k),
+        ctypes.cast(ctypes.pointer(al), ctypes.c_void_p), ctypes.c_void_p(a.data_ptr()), int(lda), int(stridea),
+        ctypes.c_void_p(b.data_ptr()), int(ldb), int(strideb),
+        ctypes.cast(ctypes.pointer(be), ctypes.c_void_p), ctypes.c_void_p(c.data_ptr()), int(ldc), int(stridec),
+        int(batch_size), int(batch_type))
+    _check(sb_handle, st)
+
+
+def _gemm(sb_handle, _TransA, _TransB, _M, _N, _K, _alpha, a_, _lda, b_, _ldb, _beta, _C, _ldc) -> None:
+    """C <- alpha*op(A)*op(B) + beta*C   (gemm_interface.hpp:189-198: strides 0, batch 1)."""
+    _gemm_backend(sb_handle, _TransA, _TransB, _M, _N, _K, _alpha, a_, _lda, 0, b_, _ldb, 0, _beta, _C, _ldc, 0,
+                  1, gemm_batch_type_t.strided)
+
+
+def _gemm_batched(sb_handle, _TransA, _TransB, _M, _N, _K, _alpha, a_, _lda, b_, _ldb, _beta, _C, _ldc,
+                  batch_size, batch_type: gemm_batch_type_t = gemm_batch_type_t.strided) -> None:
+    """Default strides = matrix footprints for strided; 0 for interleaved (gemm_interface.hpp:202-226)."""
+    sa = sb = sc = 0
+    if batch_type == gemm_batch_type_t.strided:
+        sa = (_M if str(_TransA).lower() != "n" else _K) * _lda
+        sb = (_K if str(_TransB).lower() != "n" else _N) * _ldb
+        sc = _ldc * _N
+    _gemm_backend(sb_handle, _TransA, _TransB, _M, _N, _K, _alpha, a_, _lda, sa, b_, _ldb, sb, _beta, _C, _ldc, sc,
+                  batch_size, batch_type)
+
+
+def _gemm_strided_batched(sb_handle, _TransA, _TransB, _M, _N, _K, _alpha, a_, _lda, _stridea, b_, _ldb,
+                          _strideb, _beta, _C, _ldc, _stridec, batch_size) -> None:
+    """User strides straight through (gemm_interface.hpp:230-240)."""
+    _gemm_backend(sb_handle, _TransA, _TransB, _M, _N, _K, _alpha, a_, _lda, _stridea, b_, _ldb, _strideb, _beta,
+                  _C, _ldc, _stridec, batch_size, gemm_batch_type_t.strided)
+
+
+def gemm_host(sb_handle: SB_Handle, transa, transb, m, n, k, alpha, a_host: torch.Tensor, lda, b_host, ldb, beta,
+              c_host, ldc, *, stridea=0, strideb=0, stridec=0, batch_size=1,
+              batch_type=gemm_batch_type_t.strided) -> None:
+    """HOST buffers in, HOST result out (copy_to_device + _gemm + copy_to_host + wait,
+    reference samples/gemm.cpp:50-66).  Used for the end-to-end metric."""
+    dt = _dtype_of(a_host, b_host, c_host)
+    al, be = _scalar(dt, float(alpha)), _scalar(dt, float(beta))
+    st = sb_handle._lib.pbx_gemm_host(
+        sb_handle._h, dt, str(transa).encode()[:1], str(transb).encode()[:1], int(m), int(n), int(k),
+        ctypes.cast(ctypes.pointer(al), ctypes.c_void_p), ctypes.c_void_p(a_host.data_ptr()), int(lda), int(stridea),
+        ctypes.c_void_p(b_host.data_ptr()), int(ldb), int(strideb),
+        ctypes.cast(ctypes.pointer(be), ctypes.c_void_p), ctypes.c_void_p(c_host.data_ptr()), int(ldc), int(stridec),
+        int(batch_size), int(batch_type))
+    _check(sb_handle, st)

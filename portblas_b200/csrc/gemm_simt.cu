@@ -1,0 +1,343 @@
+// gemm_simt.cu -- CUDA-core kernels of the GEMM path:
+//   * gemm_simt_kernel       : shared-memory tiled GEMM for ANY alignment / ld / transpose.
+//                              It is the shape-robust member of the family (the role
+//                              Gemm<...local...> plays in the reference,
+//                              src/operations/blas3/gemm_local.hpp:263-355,427-517) and takes
+//                              the calls the TMA/tcgen05 path cannot (unaligned base, odd ld).
+//   * gemm_interleaved_kernel: batch-interleaved layout, batch is the fastest dimension
+//                              (reference src/operations/blas3/gemm_interleaved.hpp:219-312).
+//   * scal_matrix_kernel     : C <- beta*C  (reference blas1_interface.hpp:438-510).
+//   * splitk_reduce_kernel   : sum of K-slice partials + alpha/beta epilogue (the role of
+//                              Reduction<Add,outer> + the axpby tree in
+//                              src/sb_handle/portblas_handle.hpp:354-398).
+#include <stdio.h>
+
+#include "pbx_internal.cuh"
+
+namespace {
+
+template <typename T> struct Cvt;
+template <> struct Cvt<float> {
+  __device__ static float to_f(float v) { return v; }
+  __device__ static float from_f(float v) { return v; }
+};
+template <> struct Cvt<double> {
+  __device__ static double to_f(double v) { return v; }
+  __device__ static double from_f(double v) { return v; }
+};
+template <> struct Cvt<__half> {
+  __device__ static float to_f(__half v) { return __half2float(v); }
+  __device__ static __half from_f(float v) { return __float2half_rn(v); }
+};
+template <> struct Cvt<__nv_bfloat16> {
+  __device__ static float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+  __device__ static __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+};
+
+struct SimtParams {
+  const void* A;
+  const void* B;
+  void* C;
+  void* ws;  // split-K partials (TAcc)
+  int64_t a_rs, a_cs, b_rs, b_cs;  // op(A)(m,k) = A[m*a_rs + k*a_cs], op(B)(k,n) = B[k*b_rs + n*b_cs]
+  int64_t m, n, k, ldc, sa, sb, sc, batch;
+  int64_t k_per_slice;
+  int slices, m_tiles, n_tiles;
+  double alpha, beta;
+};
+
+constexpr int SBM = 64, SBN = 64, SBK = 16;
+
+template <typename TIn, typename TOut, typename TAcc>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(SimtParams p) {
+  __shared__ TAcc As[SBK][SBM + 4];
+  __shared__ TAcc Bs[SBK][SBN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int mt = blockIdx.x % p.m_tiles, nt = blockIdx.x / p.m_tiles;
+  const int64_t m0 = (int64_t)mt * SBM, n0 = (int64_t)nt * SBN;
+  const int slice = blockIdx.y;
+  const int64_t kbeg = (int64_t)slice * p.k_per_slice;
+  const int64_t kend = min(p.k, kbeg + p.k_per_slice);
+  const bool a_mcontig = (p.a_rs == 1);
+  const bool b_kcontig = (p.b_rs == 1);
+
+  for (int64_t b = blockIdx.z; b < p.batch; b += gridDim.z) {
+    const TIn* A = reinterpret_cast<const TIn*>(p.A) + b * p.sa;
+    const TIn* B = reinterpret_cast<const TIn*>(p.B) + b * p.sb;
+    TAcc acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = TAcc(0);
+
+    for (int64_t k0 = kbeg; k0 < kend; k0 += SBK) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int e = tid + i * 256;
+        int mm, kk;
+        if (a_mcontig) { mm = e % SBM; kk = e / SBM; } else { kk = e % SBK; mm = e / SBK; }
+        TAcc v = TAcc(0);
+        if (m0 + mm < p.m && k0 + kk < kend)
+          v = (TAcc)Cvt<TIn>::to_f(A[(m0 + mm) * p.a_rs + (k0 + kk) * p.a_cs]);
+        As[kk][mm] = v;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int e = tid + i * 256;
+        int nn, kk;
+        if (b_kcontig) { kk = e % SBK; nn = e / SBK; } else { nn = e % SBN; kk = e / SBN; }
+        TAcc v = TAcc(0);
+        if (n0 + nn < p.n && k0 + kk < kend)
+          v = (TAcc)Cvt<TIn>::to_f(B[(k0 + kk) * p.b_rs + (n0 + nn) * p.b_cs]);
+        Bs[kk][nn] = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < SBK; ++kk) {
+        TAcc a[4], bb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = As[kk][tx * 4 + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bb[j] = Bs[kk][ty * 4 + j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], bb[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+
+    if (p.slices > 1) {
+      TAcc* ws = reinterpret_cast<TAcc*>(p.ws) + ((b * p.slices + slice) * p.n) * p.m;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t nn = n0 + ty * 4 + j;
+        if (nn >= p.n) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int64_t mm = m0 + tx * 4 + i;
+          if (mm < p.m) ws[nn * p.m + mm] = acc[i][j];
+        }
+      }
+    } else {
+      TOut* C = reinterpret_cast<TOut*>(p.C) + b * p.sc;
+      const TAcc alpha = (TAcc)p.alpha, beta = (TAcc)p.beta;
+      const bool beta0 = (p.beta == 0.0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t nn = n0 + ty * 4 + j;
+        if (nn >= p.n) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int64_t mm = m0 + tx * 4 + i;
+          if (mm >= p.m) continue;
+          TOut* dst = C + mm + nn * p.ldc;
+          TAcc r = alpha * acc[i][j];
+          if (!beta0) r += beta * (TAcc)Cvt<TOut>::to_f(*dst);
+          *dst = Cvt<TOut>::from_f(r);
+        }
+      }
+    }
+  }
+}
+
+// ---- interleaved batch ------------------------------------------------------
+struct IlvParams {
+  const void* A;
+  const void* B;
+  void* C;
+  int64_t a_rs, a_cs, b_rs, b_cs;  // in elements of the *interleaved* matrix (before x batch)
+  int64_t m, n, k, ldc, batch;
+  int64_t m_tiles, n_tiles;
+  double alpha, beta;
+};
+
+template <typename TIn, typename TOut, typename TAcc>
+__global__ void __launch_bounds__(256) gemm_interleaved_kernel(IlvParams p) {
+  // one thread = one batch entry x one 4x4 output tile; consecutive threads walk the batch
+  // index, which is the contiguous dimension of the interleaved layout.
+  const int64_t total = p.batch * p.m_tiles * p.n_tiles;
+  for (int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+       gid += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = gid % p.batch;
+    const int64_t t = gid / p.batch;
+    const int64_t m0 = (t % p.m_tiles) * 4, n0 = (t / p.m_tiles) * 4;
+    const TIn* A = reinterpret_cast<const TIn*>(p.A) + b;
+    const TIn* B = reinterpret_cast<const TIn*>(p.B) + b;
+    TAcc acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = TAcc(0);
+    for (int64_t kk = 0; kk < p.k; ++kk) {
+      TAcc a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        a[i] = (m0 + i < p.m) ? (TAcc)Cvt<TIn>::to_f(A[((m0 + i) * p.a_rs + kk * p.a_cs) * p.batch]) : TAcc(0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        bb[j] = (n0 + j < p.n) ? (TAcc)Cvt<TIn>::to_f(B[(kk * p.b_rs + (n0 + j) * p.b_cs) * p.batch]) : TAcc(0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], bb[j], acc[i][j]);
+    }
+    TOut* C = reinterpret_cast<TOut*>(p.C) + b;
+    const TAcc alpha = (TAcc)p.alpha, beta = (TAcc)p.beta;
+    const bool beta0 = (p.beta == 0.0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (m0 + i >= p.m || n0 + j >= p.n) continue;
+        TOut* dst = C + ((n0 + j) * p.ldc + (m0 + i)) * p.batch;
+        TAcc r = alpha * acc[i][j];
+        if (!beta0) r += beta * (TAcc)Cvt<TOut>::to_f(*dst);
+        *dst = Cvt<TOut>::from_f(r);
+      }
+  }
+}
+
+// ---- C <- beta*C ---------------------------------------------------------------
+template <typename TOut, typename TAcc>
+__global__ void __launch_bounds__(256) scal_matrix_kernel(TOut* C, int64_t m, int64_t n, int64_t ldc,
+                                                          int64_t sc, int64_t batch, double beta_d) {
+  const TAcc beta = (TAcc)beta_d;
+  const bool beta0 = (beta_d == 0.0);
+  const int64_t per = m * n;
+  const int64_t total = per * batch;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / per, r = i % per;
+    TOut* dst = C + b * sc + (r % m) + (r / m) * ldc;
+    // beta == 0 stores exact zeros without reading C (blas1_interface.hpp:444-448)
+    *dst = beta0 ? Cvt<TOut>::from_f(TAcc(0)) : Cvt<TOut>::from_f(beta * (TAcc)Cvt<TOut>::to_f(*dst));
+  }
+}
+
+// ---- split-K epilogue ------------------------------------------------------------
+template <typename TOut, typename TAcc>
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const TAcc* __restrict__ ws, TOut* C,
+                                                            int64_t m, int64_t n, int64_t ldc,
+                                                            int64_t sc, int64_t batch, int slices,
+                                                            double alpha_d, double beta_d) {
+  const TAcc alpha = (TAcc)alpha_d, beta = (TAcc)beta_d;
+  const bool beta0 = (beta_d == 0.0);
+  const int64_t per = m * n;
+  const int64_t total = per * batch;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / per, r = i % per;
+    const TAcc* src = ws + b * slices * per + r;
+    TAcc s = TAcc(0);
+    for (int sl = 0; sl < slices; ++sl) s += src[(int64_t)sl * per];  // fixed order: deterministic
+    TOut* dst = C + b * sc + (r % m) + (r / m) * ldc;
+    TAcc v = alpha * s;
+    if (!beta0) v += beta * (TAcc)Cvt<TOut>::to_f(*dst);
+    *dst = Cvt<TOut>::from_f(v);
+  }
+}
+
+template <typename F>
+int dispatch_dtype(int dtype, F&& f) {
+  switch (dtype) {
+    case PBX_F32: return f((float*)0, (float*)0, (float*)0);
+    case PBX_F64: return f((double*)0, (double*)0, (double*)0);
+    case PBX_F16: return f((__half*)0, (__half*)0, (float*)0);
+    case PBX_F16_F32: return f((__half*)0, (float*)0, (float*)0);
+    case PBX_BF16: return f((__nv_bfloat16*)0, (__nv_bfloat16*)0, (float*)0);
+    case PBX_BF16_F32: return f((__nv_bfloat16*)0, (float*)0, (float*)0);
+  }
+  return PBX_ERR_INVALID_ARG;
+}
+
+}  // namespace
+
+int pbx_launch_simt(pbx_handle_t h, const PbxGemmCall& c, int slices) {
+  SimtParams p;
+  p.A = c.A; p.B = c.B; p.C = c.C; p.ws = h->ws;
+  p.a_rs = c.ta ? c.lda : 1; p.a_cs = c.ta ? 1 : c.lda;
+  p.b_rs = c.tb ? c.ldb : 1; p.b_cs = c.tb ? 1 : c.ldb;
+  p.m = c.m; p.n = c.n; p.k = c.k; p.ldc = c.ldc;
+  p.sa = c.sa; p.sb = c.sb; p.sc = c.sc; p.batch = c.batch;
+  p.slices = slices;
+  int64_t kps = (c.k + slices - 1) / slices;
+  kps = ((kps + SBK - 1) / SBK) * SBK;
+  p.k_per_slice = kps;
+  p.m_tiles = (int)((c.m + SBM - 1) / SBM);
+  p.n_tiles = (int)((c.n + SBN - 1) / SBN);
+  p.alpha = c.alpha; p.beta = c.beta;
+  dim3 grid((unsigned)(p.m_tiles * (int64_t)p.n_tiles), (unsigned)slices,
+            (unsigned)(c.batch < 65535 ? c.batch : 65535));
+  return dispatch_dtype(c.dtype, [&](auto* ti, auto* to, auto* ta) -> int {
+    using TIn = std::remove_pointer_t<decltype(ti)>;
+    using TOut = std::remove_pointer_t<decltype(to)>;
+    using TAcc = std::remove_pointer_t<decltype(ta)>;
+    gemm_simt_kernel<TIn, TOut, TAcc><<<grid, 256, 0, h->stream>>>(p);
+    h->launches++;
+    PBX_CUDA_CHECK(h, cudaGetLastError());
+    return PBX_OK;
+  });
+}
+
+int pbx_launch_interleaved(pbx_handle_t h, const PbxGemmCall& c) {
+  IlvParams p;
+  p.A = c.A; p.B = c.B; p.C = c.C;
+  p.a_rs = c.ta ? c.lda : 1; p.a_cs = c.ta ? 1 : c.lda;
+  p.b_rs = c.tb ? c.ldb : 1; p.b_cs = c.tb ? 1 : c.ldb;
+  p.m = c.m; p.n = c.n; p.k = c.k; p.ldc = c.ldc; p.batch = c.batch;
+  p.m_tiles = (c.m + 3) / 4; p.n_tiles = (c.n + 3) / 4;
+  p.alpha = c.alpha; p.beta = c.beta;
+  const int64_t total = p.batch * p.m_tiles * p.n_tiles;
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)h->sm_count * 32;
+  if (blocks > cap) blocks = cap;
+  return dispatch_dtype(c.dtype, [&](auto* ti, auto* to, auto* ta) -> int {
+    using TIn = std::remove_pointer_t<decltype(ti)>;
+    using TOut = std::remove_pointer_t<decltype(to)>;
+    using TAcc = std::remove_pointer_t<decltype(ta)>;
+    gemm_interleaved_kernel<TIn, TOut, TAcc><<<(unsigned)blocks, 256, 0, h->stream>>>(p);
+    h->launches++;
+    PBX_CUDA_CHECK(h, cudaGetLastError());
+    return PBX_OK;
+  });
+}
+
+int pbx_launch_scal(pbx_handle_t h, int dtype, int64_t m, int64_t n, double beta, void* C,
+                    int64_t ldc, int64_t stridec, int64_t batch, int interleaved) {
+  if (interleaved) {
+    // (c*ldc + r)*batch + b  ==  column-major matrix with m*batch rows and ld = ldc*batch
+    m = m * batch; ldc = ldc * batch; batch = 1; stridec = 0;
+  }
+  const int64_t total = m * n * batch;
+  if (total == 0) return PBX_OK;
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)h->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  return dispatch_dtype(dtype, [&](auto* ti, auto* to, auto* ta) -> int {
+    using TOut = std::remove_pointer_t<decltype(to)>;
+    using TAcc = std::remove_pointer_t<decltype(ta)>;
+    scal_matrix_kernel<TOut, TAcc><<<(unsigned)blocks, 256, 0, h->stream>>>(
+        (TOut*)C, m, n, ldc, stridec, batch, beta);
+    h->launches++;
+    PBX_CUDA_CHECK(h, cudaGetLastError());
+    return PBX_OK;
+  });
+}
+
+int pbx_launch_splitk_reduce(pbx_handle_t h, const PbxGemmCall& c, int slices) {
+  const int64_t total = c.m * c.n * c.batch;
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)h->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  return dispatch_dtype(c.dtype, [&](auto* ti, auto* to, auto* ta) -> int {
+    using TOut = std::remove_pointer_t<decltype(to)>;
+    using TAcc = std::remove_pointer_t<decltype(ta)>;
+    splitk_reduce_kernel<TOut, TAcc><<<(unsigned)blocks, 256, 0, h->stream>>>(
+        (const TAcc*)h->ws, (TOut*)c.C, c.m, c.n, c.ldc, c.sc, c.batch, slices, c.alpha, c.beta);
+    h->launches++;
+    PBX_CUDA_CHECK(h, cudaGetLastError());
+    return PBX_OK;
+  });
+}

@@ -1,0 +1,361 @@
+// pbx_api.cu -- C-ABI entry points, front-end rules and the kernel selector.
+//
+// Front-end restated from reference src/interface/gemm_interface.hpp:105-185
+// (alpha==0 shortcut first, then trans/stride validation, then beta==0
+// specialisation).  The selector replaces
+// src/interface/blas3/backend/nvidia_gpu.hpp:40-260.
+#include <ctype.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "pbx_internal.cuh"
+
+extern "C" {
+
+const char* pbx_status_string(int status) {
+  switch (status) {
+    case PBX_OK: return "ok";
+    case PBX_ERR_INVALID_TRANSA: return "invalid _TransA";
+    case PBX_ERR_INVALID_TRANSB: return "invalid _TransB";
+    case PBX_ERR_INVALID_STRIDEC: return "invalid _stridec";
+    case PBX_ERR_INVALID_STRIDEA: return "invalid _stridea";
+    case PBX_ERR_INVALID_STRIDEB: return "invalid _strideb";
+    case PBX_ERR_INVALID_ARG: return "invalid argument";
+    case PBX_ERR_CUDA: return "CUDA error";
+    case PBX_ERR_NO_DEVICE: return "no sm_100 CUDA device (this library has no CPU fallback)";
+    case PBX_ERR_WORKSPACE: return "workspace allocation failed";
+  }
+  return "unknown status";
+}
+
+int pbx_create(pbx_handle_t* out, int device_ordinal, void* cuda_stream) {
+  if (!out) return PBX_ERR_INVALID_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device_ordinal >= ndev ||
+      device_ordinal < 0) {
+    fprintf(stderr, "[pbx_gemm] %s\n", pbx_status_string(PBX_ERR_NO_DEVICE));
+    return PBX_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device_ordinal) != cudaSuccess) return PBX_ERR_CUDA;
+  if (prop.major != 10) {
+    fprintf(stderr, "[pbx_gemm] device %d is sm_%d%d; this library is built for sm_100a only\n",
+            device_ordinal, prop.major, prop.minor);
+    return PBX_ERR_NO_DEVICE;
+  }
+  pbx_handle_s* h = new pbx_handle_s();
+  h->device = device_ordinal;
+  h->stream = (cudaStream_t)cuda_stream;
+  h->sm_count = prop.multiProcessorCount;
+  h->cc_major = prop.major;
+  h->cc_minor = prop.minor;
+  const char* fk = getenv("PBX_FORCE_KERNEL");
+  if (fk) h->forced_kernel = atoi(fk);
+  if (cudaSetDevice(device_ordinal) != cudaSuccess) { delete h; return PBX_ERR_CUDA; }
+  *out = h;
+  return PBX_OK;
+}
+
+int pbx_destroy(pbx_handle_t h) {
+  if (!h) return PBX_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  if (h->ws) cudaFree(h->ws);
+  for (int i = 0; i < 3; ++i)
+    if (h->stage[i]) cudaFree(h->stage[i]);
+  delete h;
+  return PBX_OK;
+}
+
+int pbx_set_stream(pbx_handle_t h, void* s) { if (!h) return PBX_ERR_INVALID_ARG; h->stream = (cudaStream_t)s; return PBX_OK; }
+void* pbx_get_stream(pbx_handle_t h) { return h ? (void*)h->stream : nullptr; }
+int pbx_get_num_compute_units(pbx_handle_t h) { return h ? h->sm_count : 0; }
+int pbx_get_device(pbx_handle_t h) { return h ? h->device : -1; }
+int pbx_synchronize(pbx_handle_t h) {
+  if (!h) return PBX_ERR_INVALID_ARG;
+  PBX_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  return PBX_OK;
+}
+const char* pbx_last_error(pbx_handle_t h) { return h ? h->last_error.c_str() : "null handle"; }
+int pbx_set_forced_kernel(pbx_handle_t h, int k) { if (!h) return PBX_ERR_INVALID_ARG; h->forced_kernel = k; return PBX_OK; }
+int pbx_set_split_k(pbx_handle_t h, int s) { if (!h || s < 0) return PBX_ERR_INVALID_ARG; h->forced_split_k = s; return PBX_OK; }
+int pbx_last_kernel(pbx_handle_t h) { return h ? h->last_kernel : PBX_KERNEL_NONE; }
+int pbx_last_split_k(pbx_handle_t h) { return h ? h->last_split_k : 0; }
+int64_t pbx_launch_count(pbx_handle_t h) { return h ? h->launches : 0; }
+int64_t pbx_workspace_bytes(pbx_handle_t h) { return h ? h->ws_bytes : 0; }
+
+}  // extern "C"
+
+int pbx_ensure_workspace(pbx_handle_t h, int64_t bytes) {
+  if (bytes <= h->ws_bytes) return PBX_OK;
+  // The previous buffer may still be in use by work queued on the stream.
+  if (h->ws) {
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaFree(h->ws) != cudaSuccess) {
+      h->last_error = "workspace free failed";
+      return PBX_ERR_WORKSPACE;
+    }
+    h->ws = nullptr; h->ws_bytes = 0;
+  }
+  const int64_t rounded = ((bytes + (1 << 20) - 1) >> 20) << 20;
+  if (cudaMalloc(&h->ws, (size_t)rounded) != cudaSuccess) {
+    cudaGetLastError();
+    h->last_error = "workspace allocation failed";
+    return PBX_ERR_WORKSPACE;
+  }
+  h->ws_bytes = rounded;
+  return PBX_OK;
+}
+
+// ---- split-K policy -------------------------------------------------------------
+// The reference rule is depth = ceil(4*CUs / (ceil(M/tm)*ceil(N/tn))) and "no split when
+// depth == 1 || K <= 2048" (gemm_partial_local.hpp:191-199, portblas_handle.hpp:323).  On
+// B200 the quantity that matters is wave quantisation of 148 SMs: split only when the
+// output tiles cannot fill the machine and every slice still has a deep K loop.
+static int choose_split_k(pbx_handle_t h, const PbxGemmCall& c, int tile_m, int tile_n,
+                          int64_t k_block, int64_t min_k_per_slice) {
+  if (h->forced_split_k == 1) return 1;
+  const int64_t kb = (c.k + k_block - 1) / k_block;
+  int slices = 1;
+  if (h->forced_split_k > 1) {
+    slices = h->forced_split_k;
+  } else {
+    const int64_t tiles = ((c.m + tile_m - 1) / tile_m) * ((c.n + tile_n - 1) / tile_n) * c.batch;
+    if (tiles * 2 > h->sm_count || c.k < 2 * min_k_per_slice) return 1;
+    // as many whole waves of CTAs as the K depth allows, at most 2 waves
+    int64_t want = (2 * (int64_t)h->sm_count) / tiles;
+    int64_t maxs = c.k / min_k_per_slice;
+    slices = (int)(want < maxs ? want : maxs);
+    if (slices < 1) slices = 1;
+  }
+  if (slices > kb) slices = (int)kb;
+  if (slices < 1) slices = 1;
+  // drop empty trailing slices
+  const int64_t kbps = (kb + slices - 1) / slices;
+  slices = (int)((kb + kbps - 1) / kbps);
+  return slices;
+}
+
+static int run_gemm(pbx_handle_t h, const PbxGemmCall& c, int batch_type) {
+  int kernel = h->forced_kernel;
+  if (batch_type == 1 && c.batch > 1) {
+    kernel = PBX_KERNEL_INTERLEAVED;
+  } else if (kernel == PBX_KERNEL_AUTO || kernel == PBX_KERNEL_INTERLEAVED) {
+    if (c.dtype == PBX_F64) {
+      kernel = PBX_KERNEL_DMMA;
+    } else if (pbx_tcgen05_eligible(h, c)) {
+      // tiny problems are launch-latency bound either way; the 128-row MMA tile wastes
+      // most of its lanes below ~32 rows, keep those on the CUDA-core kernel.
+      kernel = (c.m * c.n < 64 * 64 && c.k < 4096) ? PBX_KERNEL_SIMT : PBX_KERNEL_TCGEN05;
+    } else {
+      kernel = PBX_KERNEL_SIMT;
+    }
+  }
+  if (kernel == PBX_KERNEL_TCGEN05 && (c.dtype == PBX_F64 || !pbx_tcgen05_eligible(h, c)))
+    kernel = (c.dtype == PBX_F64) ? PBX_KERNEL_DMMA : PBX_KERNEL_SIMT;
+  if (kernel == PBX_KERNEL_DMMA && c.dtype != PBX_F64) kernel = PBX_KERNEL_SIMT;
+
+  h->last_kernel = kernel;
+  h->last_split_k = 1;
+  int st = PBX_OK;
+  if (kernel == PBX_KERNEL_INTERLEAVED) return pbx_launch_interleaved(h, c);
+
+  int slices = 1;
+  const size_t acc_size = (c.dtype == PBX_F64) ? 8 : 4;
+  if (kernel == PBX_KERNEL_TCGEN05) slices = choose_split_k(h, c, 128, 128, c.dtype == PBX_F32 ? 32 : 64, 2048);
+  else if (kernel == PBX_KERNEL_DMMA) slices = choose_split_k(h, c, 128, 128, 16, 1024);
+  else slices = choose_split_k(h, c, 64, 64, 16, 1024);
+  if (slices > 1) {
+    st = pbx_ensure_workspace(h, (int64_t)acc_size * c.m * c.n * c.batch * slices);
+    if (st != PBX_OK) return st;
+  }
+  h->last_split_k = slices;
+  if (kernel == PBX_KERNEL_TCGEN05) st = pbx_launch_tcgen05(h, c, slices);
+  else if (kernel == PBX_KERNEL_DMMA) st = pbx_launch_dmma(h, c, slices);
+  else st = pbx_launch_simt(h, c, slices);
+  if (st != PBX_OK) return st;
+  if (slices > 1) st = pbx_launch_splitk_reduce(h, c, slices);
+  return st;
+}
+
+static bool valid_dtype(int d) { return d >= PBX_F32 && d <= PBX_BF16_F32; }
+
+static double read_scalar(int dtype, const void* p) {
+  return dtype == PBX_F64 ? *reinterpret_cast<const double*>(p)
+                          : (double)*reinterpret_cast<const float*>(p);
+}
+
+extern "C" {
+
+int pbx_scal_matrix(pbx_handle_t h, int dtype, int64_t m, int64_t n, const void* beta, void* C,
+                    int64_t ldc, int64_t stridec, int64_t batch) {
+  if (!h || !valid_dtype(dtype) || !beta || m < 0 || n < 0 || batch < 0) return PBX_ERR_INVALID_ARG;
+  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  const double b = read_scalar(dtype, beta);
+  h->last_split_k = 1;
+  if (b == 1.0 || m == 0 || n == 0 || batch == 0) {  // blas1_interface.hpp:498-499
+    h->last_kernel = PBX_KERNEL_NONE;
+    return PBX_OK;
+  }
+  h->last_kernel = PBX_KERNEL_SCAL;
+  return pbx_launch_scal(h, dtype, m, n, b, C, ldc, stridec, batch, 0);
+}
+
+int pbx_gemm(pbx_handle_t h, int dtype, char transa, char transb, int64_t m, int64_t n, int64_t k,
+             const void* alpha, const void* A, int64_t lda, int64_t stridea, const void* B,
+             int64_t ldb, int64_t strideb, const void* beta, void* C, int64_t ldc, int64_t stridec,
+             int64_t batch, int batch_type) {
+  if (!h) return PBX_ERR_INVALID_ARG;
+  if (!valid_dtype(dtype) || !alpha || !beta || m < 0 || n < 0 || k < 0 || batch < 0 ||
+      (batch_type != 0 && batch_type != 1)) {
+    h->last_error = "pbx_gemm: invalid argument";
+    return PBX_ERR_INVALID_ARG;
+  }
+  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  const double al = read_scalar(dtype, alpha);
+  const double be = read_scalar(dtype, beta);
+  h->last_split_k = 1;
+
+  // (1) alpha == 0 comes first, before any validation (gemm_interface.hpp:112-139).
+  if (al == 0.0) {
+    if (m == 0 || n == 0 || batch == 0 || be == 1.0) { h->last_kernel = PBX_KERNEL_NONE; return PBX_OK; }
+    h->last_kernel = PBX_KERNEL_SCAL;
+    return pbx_launch_scal(h, dtype, m, n, be, C, ldc, stridec, batch, batch_type == 1 && batch > 1);
+  }
+  // (2) trans validation (gemm_interface.hpp:141-148); 'c' == 't' for real types (:150-151)
+  const int ta_c = tolower((unsigned char)transa), tb_c = tolower((unsigned char)transb);
+  if (ta_c != 'n' && ta_c != 't' && ta_c != 'c') return PBX_ERR_INVALID_TRANSA;
+  if (tb_c != 'n' && tb_c != 't' && tb_c != 'c') return PBX_ERR_INVALID_TRANSB;
+  // (3) stride validation, only for strided batches (gemm_interface.hpp:153-166)
+  if (batch > 1 && batch_type == 0) {
+    if (stridec < ldc * n || stridec < 0) return PBX_ERR_INVALID_STRIDEC;
+    if (stridea < 0) return PBX_ERR_INVALID_STRIDEA;
+    if (strideb < 0) return PBX_ERR_INVALID_STRIDEB;
+  }
+  if (m == 0 || n == 0 || batch == 0) { h->last_kernel = PBX_KERNEL_NONE; return PBX_OK; }
+  if (k == 0) {  // BLAS: C <- beta*C
+    if (be == 1.0) { h->last_kernel = PBX_KERNEL_NONE; return PBX_OK; }
+    h->last_kernel = PBX_KERNEL_SCAL;
+    return pbx_launch_scal(h, dtype, m, n, be, C, ldc, stridec, batch, batch_type == 1 && batch > 1);
+  }
+  if (!A || !B || !C) { h->last_error = "pbx_gemm: null matrix pointer"; return PBX_ERR_INVALID_ARG; }
+
+  PbxGemmCall c;
+  c.dtype = dtype; c.ta = (ta_c != 'n'); c.tb = (tb_c != 'n');
+  c.m = m; c.n = n; c.k = k; c.alpha = al; c.beta = be;
+  c.A = A; c.B = B; c.C = C; c.lda = lda; c.ldb = ldb; c.ldc = ldc;
+  c.sa = (batch > 1) ? stridea : 0; c.sb = (batch > 1) ? strideb : 0; c.sc = (batch > 1) ? stridec : 0;
+  c.batch = batch;
+  return run_gemm(h, c, batch_type);
+}
+
+int pbx_sgemm(pbx_handle_t h, char ta, char tb, int64_t m, int64_t n, int64_t k, const float* alpha,
+              const float* A, int64_t lda, int64_t sa, const float* B, int64_t ldb, int64_t sb,
+              const float* beta, float* C, int64_t ldc, int64_t sc, int64_t batch, int bt) {
+  return pbx_gemm(h, PBX_F32, ta, tb, m, n, k, alpha, A, lda, sa, B, ldb, sb, beta, C, ldc, sc, batch, bt);
+}
+int pbx_dgemm(pbx_handle_t h, char ta, char tb, int64_t m, int64_t n, int64_t k, const double* alpha,
+              const double* A, int64_t lda, int64_t sa, const double* B, int64_t ldb, int64_t sb,
+              const double* beta, double* C, int64_t ldc, int64_t sc, int64_t batch, int bt) {
+  return pbx_gemm(h, PBX_F64, ta, tb, m, n, k, alpha, A, lda, sa, B, ldb, sb, beta, C, ldc, sc, batch, bt);
+}
+int pbx_hgemm(pbx_handle_t h, char ta, char tb, int64_t m, int64_t n, int64_t k, const float* alpha,
+              const void* A, int64_t lda, int64_t sa, const void* B, int64_t ldb, int64_t sb,
+              const float* beta, void* C, int64_t ldc, int64_t sc, int64_t batch, int bt) {
+  return pbx_gemm(h, PBX_F16, ta, tb, m, n, k, alpha, A, lda, sa, B, ldb, sb, beta, C, ldc, sc, batch, bt);
+}
+int pbx_hsgemm(pbx_handle_t h, char ta, char tb, int64_t m, int64_t n, int64_t k, const float* alpha,
+               const void* A, int64_t lda, int64_t sa, const void* B, int64_t ldb, int64_t sb,
+               const float* beta, float* C, int64_t ldc, int64_t sc, int64_t batch, int bt) {
+  return pbx_gemm(h, PBX_F16_F32, ta, tb, m, n, k, alpha, A, lda, sa, B, ldb, sb, beta, C, ldc, sc, batch, bt);
+}
+int pbx_bf16gemm(pbx_handle_t h, char ta, char tb, int64_t m, int64_t n, int64_t k, const float* alpha,
+                 const void* A, int64_t lda, int64_t sa, const void* B, int64_t ldb, int64_t sb,
+                 const float* beta, void* C, int64_t ldc, int64_t sc, int64_t batch, int bt) {
+  return pbx_gemm(h, PBX_BF16, ta, tb, m, n, k, alpha, A, lda, sa, B, ldb, sb, beta, C, ldc, sc, batch, bt);
+}
+
+// ---- memory helpers ------------------------------------------------------------------
+int pbx_malloc(pbx_handle_t h, void** dptr, int64_t bytes) {
+  if (!h || !dptr || bytes < 0) return PBX_ERR_INVALID_ARG;
+  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  PBX_CUDA_CHECK(h, cudaMalloc(dptr, (size_t)(bytes > 0 ? bytes : 1)));
+  return PBX_OK;
+}
+int pbx_free(pbx_handle_t h, void* dptr) {
+  if (!h) return PBX_ERR_INVALID_ARG;
+  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  PBX_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  PBX_CUDA_CHECK(h, cudaFree(dptr));
+  return PBX_OK;
+}
+int pbx_copy_to_device(pbx_handle_t h, const void* src, void* dst, int64_t bytes) {
+  if (!h || bytes < 0) return PBX_ERR_INVALID_ARG;
+  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  PBX_CUDA_CHECK(h, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, h->stream));
+  return PBX_OK;
+}
+int pbx_copy_to_host(pbx_handle_t h, const void* src, void* dst, int64_t bytes) {
+  if (!h || bytes < 0) return PBX_ERR_INVALID_ARG;
+  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  PBX_CUDA_CHECK(h, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, h->stream));
+  return PBX_OK;
+}
+int pbx_fill_bytes(pbx_handle_t h, void* dst, int value, int64_t bytes) {
+  if (!h || bytes < 0) return PBX_ERR_INVALID_ARG;
+  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  PBX_CUDA_CHECK(h, cudaMemsetAsync(dst, value, (size_t)bytes, h->stream));
+  return PBX_OK;
+}
+
+// ---- host-buffer path (end-to-end metric) ------------------------------------------------
+static int ensure_stage(pbx_handle_t h, int i, int64_t bytes) {
+  if (bytes <= h->stage_bytes[i]) return PBX_OK;
+  if (h->stage[i]) {
+    PBX_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+    PBX_CUDA_CHECK(h, cudaFree(h->stage[i]));
+    h->stage[i] = nullptr; h->stage_bytes[i] = 0;
+  }
+  PBX_CUDA_CHECK(h, cudaMalloc(&h->stage[i], (size_t)bytes));
+  h->stage_bytes[i] = bytes;
+  return PBX_OK;
+}
+
+int pbx_gemm_host(pbx_handle_t h, int dtype, char transa, char transb, int64_t m, int64_t n,
+                  int64_t k, const void* alpha, const void* A_host, int64_t lda, int64_t stridea,
+                  const void* B_host, int64_t ldb, int64_t strideb, const void* beta, void* C_host,
+                  int64_t ldc, int64_t stridec, int64_t batch, int batch_type) {
+  if (!h || !valid_dtype(dtype) || !alpha || !beta || m < 0 || n < 0 || k < 0 || batch < 1)
+    return PBX_ERR_INVALID_ARG;
+  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  const bool ta = tolower((unsigned char)transa) != 'n', tb = tolower((unsigned char)transb) != 'n';
+  const int64_t a_cols = ta ? m : k, b_cols = tb ? k : n;
+  int64_t a_el, b_el, c_el;
+  if (batch_type == 1) {
+    a_el = lda * a_cols * batch; b_el = ldb * b_cols * batch; c_el = ldc * n * batch;
+  } else {
+    a_el = (batch - 1) * stridea + lda * a_cols;
+    b_el = (batch - 1) * strideb + ldb * b_cols;
+    c_el = (batch - 1) * stridec + ldc * n;
+  }
+  const int64_t a_bytes = a_el * (int64_t)pbx_in_size(dtype), b_bytes = b_el * (int64_t)pbx_in_size(dtype);
+  const int64_t c_bytes = c_el * (int64_t)pbx_out_size(dtype);
+  int st;
+  if ((st = ensure_stage(h, 0, a_bytes)) || (st = ensure_stage(h, 1, b_bytes)) ||
+      (st = ensure_stage(h, 2, c_bytes)))
+    return st;
+  const double be = read_scalar(dtype, beta);
+  PBX_CUDA_CHECK(h, cudaMemcpyAsync(h->stage[0], A_host, (size_t)a_bytes, cudaMemcpyHostToDevice, h->stream));
+  PBX_CUDA_CHECK(h, cudaMemcpyAsync(h->stage[1], B_host, (size_t)b_bytes, cudaMemcpyHostToDevice, h->stream));
+  if (be != 0.0 || ldc != m || (batch > 1 && batch_type == 0 && stridec != ldc * n))
+    PBX_CUDA_CHECK(h, cudaMemcpyAsync(h->stage[2], C_host, (size_t)c_bytes, cudaMemcpyHostToDevice, h->stream));
+  st = pbx_gemm(h, dtype, transa, transb, m, n, k, alpha, h->stage[0], lda, stridea, h->stage[1], ldb,
+                strideb, beta, h->stage[2], ldc, stridec, batch, batch_type);
+  if (st != PBX_OK) return st;
+  PBX_CUDA_CHECK(h, cudaMemcpyAsync(C_host, h->stage[2], (size_t)c_bytes, cudaMemcpyDeviceToHost, h->stream));
+  PBX_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
+  return PBX_OK;
+}
+
+}  // extern "C"

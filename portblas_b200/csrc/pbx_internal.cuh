@@ -1,0 +1,88 @@
+// pbx_internal.cuh -- shared host-side types of libpbx_gemm (not part of the ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/pbx_gemm.h"
+
+// One GEMM call after front-end normalisation: trans chars resolved, scalars
+// widened.  Layout convention: column-major, element (r,c) of a stored matrix
+// X at X[r + c*ldx].  op(A) is m x k, op(B) is k x n  (reference
+// src/interface/gemm_launcher.hpp:54-56 builds its views the same way).
+struct PbxGemmCall {
+  int dtype;
+  bool ta, tb;
+  int64_t m, n, k;
+  double alpha, beta;  // exact for float and double scalars
+  const void* A;
+  const void* B;
+  void* C;
+  int64_t lda, ldb, ldc;
+  int64_t sa, sb, sc;  // batch strides in elements (strided)
+  int64_t batch;
+};
+
+struct pbx_handle_s {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  int forced_kernel = PBX_KERNEL_AUTO;
+  int forced_split_k = 0;
+  int last_kernel = PBX_KERNEL_NONE;
+  int last_split_k = 1;
+  int64_t launches = 0;
+  std::string last_error;
+  // split-K workspace pool (stream ordered; grows monotonically)
+  void* ws = nullptr;
+  int64_t ws_bytes = 0;
+  // staging buffers for pbx_gemm_host
+  void* stage[3] = {nullptr, nullptr, nullptr};
+  int64_t stage_bytes[3] = {0, 0, 0};
+};
+
+#define PBX_CUDA_CHECK(h, expr)                                                          \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      (h)->last_error = std::string(#expr) + ": " + cudaGetErrorString(_e);              \
+      fprintf(stderr, "[pbx_gemm] CUDA error %s at %s:%d\n", (h)->last_error.c_str(),   \
+              __FILE__, __LINE__);                                                       \
+      return PBX_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+static inline size_t pbx_in_size(int dtype) {
+  switch (dtype) {
+    case PBX_F32: return 4;
+    case PBX_F64: return 8;
+    default: return 2;
+  }
+}
+static inline size_t pbx_out_size(int dtype) {
+  switch (dtype) {
+    case PBX_F32: case PBX_F16_F32: case PBX_BF16_F32: return 4;
+    case PBX_F64: return 8;
+    default: return 2;
+  }
+}
+
+int pbx_ensure_workspace(pbx_handle_t h, int64_t bytes);
+
+// ---- kernel families (each returns a pbx_status_t) -----------------------
+// slices > 1: the kernel writes raw fp32/fp64 partial sums to h->ws laid out
+// [batch][slice][n][m] (compact, m contiguous) and pbx_launch_splitk_reduce
+// applies alpha/beta.
+int pbx_launch_simt(pbx_handle_t h, const PbxGemmCall& c, int slices);
+int pbx_launch_interleaved(pbx_handle_t h, const PbxGemmCall& c);
+int pbx_launch_scal(pbx_handle_t h, int dtype, int64_t m, int64_t n, double beta, void* C,
+                    int64_t ldc, int64_t stridec, int64_t batch, int interleaved);
+int pbx_launch_splitk_reduce(pbx_handle_t h, const PbxGemmCall& c, int slices);
+bool pbx_tcgen05_eligible(pbx_handle_t h, const PbxGemmCall& c);
+int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices);
+int pbx_launch_dmma(pbx_handle_t h, const PbxGemmCall& c, int slices);

@@ -1,0 +1,95 @@
+"""Multi-GPU partitioning of the GEMM path: one process per GPU, no data-path collective.
+
+The reference is single-device (one SB_Handle == one sycl::queue,
+include/sb_handle/portblas_handle.h:51-60); sharding is new in this build:
+
+  * large GEMMs are split into M-blocks: rank g owns rows [r0, r0+rows) of op(A) and of C, B is
+    replicated.  In column-major storage a row block is just a pointer offset with the ORIGINAL
+    leading dimensions, so each rank runs an ordinary (rows x N x K) ``_gemm``;
+  * strided-batched GEMMs are split by batch range: pointer offsets b0*stride, local batch count.
+
+Both partitions are embarrassingly parallel.  The only collective is the optional gather of C
+into one buffer (``gather_c_mblocks`` / ``gather_c_batches``), NCCL all_gather over NVLink on
+GPUs (gloo on CPU in the tests).
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def split_range(total: int, world: int, rank: int, align: int = 1) -> Tuple[int, int]:
+    """[start, count) of ``rank``'s share of ``total`` units; shares are multiples of ``align``
+    except possibly the last non-empty one; earlier ranks take the remainder."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad world/rank")
+    units = (total + align - 1) // align
+    base, rem = divmod(units, world)
+    u0 = rank * base + min(rank, rem)
+    cnt = base + (1 if rank < rem else 0)
+    start = min(u0 * align, total)
+    end = min((u0 + cnt) * align, total)
+    return start, end - start
+
+
+@dataclasses.dataclass(frozen=True)
+class MBlockShard:
+    row0: int        # first row of C / op(A) owned by this rank
+    rows: int        # local M
+    a_offset: int    # element offset into A
+    c_offset: int    # element offset into C
+
+
+def shard_mblock(transa: str, m: int, lda: int, world: int, rank: int, align: int = 128) -> MBlockShard:
+    """Rows of op(A): A is stored M x K (rows contiguous) for 'n' -> offset row0;
+    stored K x M for 't' -> offset row0*lda."""
+    row0, rows = split_range(m, world, rank, align)
+    a_off = row0 if transa.lower() == "n" else row0 * lda
+    return MBlockShard(row0, rows, a_off, row0)
+
+
+@dataclasses.dataclass(frozen=True)
+class BatchShard:
+    batch0: int
+    batches: int
+    a_offset: int
+    b_offset: int
+    c_offset: int
+
+
+def shard_batch(batch: int, stridea: int, strideb: int, stridec: int, world: int, rank: int) -> BatchShard:
+    b0, cnt = split_range(batch, world, rank)
+    return BatchShard(b0, cnt, b0 * stridea, b0 * strideb, b0 * stridec)
+
+
+def gather_c_mblocks(c_local: torch.Tensor, m: int, n: int, world: int, align: int = 128, group=None) -> torch.Tensor:
+    """All-gather compact (rows x n, column-major, ld == rows) C row-blocks into a full compact
+    m x n column-major matrix on every rank."""
+    shapes = [split_range(m, world, r, align) for r in range(world)]
+    max_rows = max(s[1] for s in shapes)
+    pad = torch.zeros(max_rows * n, dtype=c_local.dtype, device=c_local.device)
+    rows = shapes[dist.get_rank(group)][1]
+    pad.view(n, max_rows)[:, :rows] = c_local.view(n, rows)
+    out: List[torch.Tensor] = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad, group=group)
+    full = torch.empty(m * n, dtype=c_local.dtype, device=c_local.device)
+    fv = full.view(n, m)
+    for r, (r0, cnt) in enumerate(shapes):
+        if cnt:
+            fv[:, r0:r0 + cnt] = out[r].view(n, max_rows)[:, :cnt]
+    return full
+
+
+def gather_c_batches(c_local: torch.Tensor, per_matrix: int, batch: int, world: int, group=None) -> torch.Tensor:
+    """All-gather contiguous batch ranges of C (stride_c == per_matrix)."""
+    shapes = [split_range(batch, world, r) for r in range(world)]
+    max_b = max(s[1] for s in shapes)
+    pad = torch.zeros(max_b * per_matrix, dtype=c_local.dtype, device=c_local.device)
+    cnt = shapes[dist.get_rank(group)][1]
+    pad[:cnt * per_matrix] = c_local[:cnt * per_matrix]
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad, group=group)
+    return torch.cat([out[r][:shapes[r][1] * per_matrix] for r in range(world)])

@@ -1,0 +1,207 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle.
+
+The parameter grids restate the reference's own GEMM test suites
+(test/unittest/blas3/blas3_gemm_test.cpp:30-141, blas3_gemm_batched_test.cpp:30-147,
+blas3_gemm_tall_skinny_test.cpp:30-103, test/unittest/joint_matrix/*.cpp) -- same shapes,
+transposes, scalars, ld multipliers, offsets, batch sizes and stride multipliers -- and run
+them for every (in,out) element-type pair of the C-ABI.
+
+Bars: the reference's almost_equal margins (float 5e-3/1e-3, double 1e-10, half 5e-2/1.0;
+common/include/common/float_comparison.hpp:101-158) AND the north-star bounds against the
+long-double truth: fp64 1e-12, fp32 (3xTF32) 1e-5, relative to |alpha||A||B| + |beta||C|.
+"""
+from __future__ import annotations
+
+import itertools
+
+import pytest
+
+from gemm_case import Case, run_case
+
+pytestmark = pytest.mark.gpu
+
+ALL_DTYPES = ["f32", "f64", "f16", "f16f32", "bf16", "bf16f32"]
+TRANS = [("n", "n"), ("n", "t"), ("t", "n"), ("t", "t")]
+SIMT, TCGEN05, DMMA = 1, 2, 3
+
+
+def _run_all(handle, cases):
+    failures = []
+    for cs in cases:
+        r = run_case(handle, cs)
+        if not r.ok:
+            failures.append(f"{cs.ident()} kernel={r.kernel} sk={r.split_k} ref_mismatch={r.ref_mismatch} "
+                            f"bound_viol={r.bound_violations} max_rel={r.max_rel_bound:.3e} {r.detail}")
+    assert not failures, f"{len(failures)}/{len(cases)} cases failed:\n" + "\n".join(failures[:20])
+
+
+# ---- Gemm suites (blas3_gemm_test.cpp) -------------------------------------------------------
+def _small_beta_nonzero(dt):
+    return [Case(dtype=dt, transa=ta, transb=tb, m=m, n=n, k=k, alpha=1.5, beta=1.5)
+            for m, n, k, (ta, tb) in itertools.product([11, 16, 32], [11, 16, 32], [16, 17], TRANS)]
+
+
+def _small_beta_zero(dt, lds):
+    return [Case(dtype=dt, transa=ta, transb=tb, m=m, n=n, k=17, alpha=1.5, beta=0.0, lda_mul=lds[0],
+                 ldb_mul=lds[1], ldc_mul=lds[2])
+            for m, n, (ta, tb) in itertools.product([11, 32], [11, 32], TRANS)]
+
+
+def _alpha_zero(dt):
+    return [Case(dtype=dt, m=16, n=16, k=17, alpha=0.0, beta=b, offset=off, lda_mul=la, ldb_mul=lb, ldc_mul=lc)
+            for off, b, la, lb, lc in itertools.product([0, 10], [0.0, 1.0], [1, 2], [1, 2], [1, 2])]
+
+
+def _offset_nonzero(dt):
+    return [Case(dtype=dt, m=m, n=n, k=k, alpha=1.0, beta=1.0, offset=off, lda_mul=la, ldb_mul=lb, ldc_mul=lc)
+            for off, m, n, k, la, lb, lc in itertools.product([1, 10], [16, 63], [16, 63], [17, 63], [1, 2], [1, 2],
+                                                              [1, 2])]
+
+
+def _large(dt, ms):
+    return [Case(dtype=dt, transa=ta, transb=tb, m=m, n=n, k=k, alpha=1.0, beta=1.0)
+            for m, n, k, (ta, tb) in itertools.product(ms, [257, 511], [253, 511], TRANS)]
+
+
+@pytest.mark.parametrize("dt", ALL_DTYPES)
+def test_gemm_small_beta_nonzero_ld_match(handle, dt):
+    _run_all(handle, _small_beta_nonzero(dt))
+
+
+@pytest.mark.parametrize("dt", ALL_DTYPES)
+def test_gemm_small_beta_zero(handle, dt):
+    _run_all(handle, _small_beta_zero(dt, (1, 1, 1)) + _small_beta_zero(dt, (2, 3, 4)))
+
+
+@pytest.mark.parametrize("dt", ALL_DTYPES)
+def test_gemm_alpha_zero(handle, dt):
+    _run_all(handle, _alpha_zero(dt))
+
+
+@pytest.mark.parametrize("dt", ALL_DTYPES)
+def test_gemm_offset_nonzero(handle, dt):
+    _run_all(handle, _offset_nonzero(dt))
+
+
+@pytest.mark.parametrize("dt", ALL_DTYPES)
+def test_gemm_large_beta_nonzero(handle, dt):
+    ms = [253, 511, 1024, 2048, 2200] if dt in ("f32", "f64") else [253, 1024, 2200]
+    _run_all(handle, _large(dt, ms))
+
+
+# ---- every kernel family on the same shapes (forced) -------------------------------------------
+@pytest.mark.parametrize("dt,kernel", [("f32", SIMT), ("f32", TCGEN05), ("f64", SIMT), ("f64", DMMA),
+                                       ("f16", SIMT), ("f16", TCGEN05), ("bf16", TCGEN05),
+                                       ("f16f32", TCGEN05), ("bf16f32", TCGEN05)])
+def test_gemm_forced_kernel(handle, dt, kernel):
+    # ld multiples of 8 elements keep TMA eligibility for every type; 2200/264 are ragged vs 128/256 tiles
+    cases = [Case(dtype=dt, transa=ta, transb=tb, m=m, n=n, k=k, alpha=1.5, beta=b, kernel=kernel)
+             for m, n, k, b, (ta, tb) in itertools.product([8, 136, 2200], [24, 264], [40, 520], [0.0, 0.5], TRANS)]
+    _run_all(handle, cases)
+    r = run_case(handle, cases[-1])
+    want = {SIMT: "simt", TCGEN05: "tcgen05", DMMA: "dmma"}[kernel]
+    assert r.kernel == want, f"forced kernel {want} not used (got {r.kernel})"
+
+
+# ---- BatchGemm suites (blas3_gemm_batched_test.cpp) ----------------------------------------------
+@pytest.mark.parametrize("dt", ALL_DTYPES)
+def test_batched_beta_nonzero_ld_match(handle, dt):
+    cases = [Case(dtype=dt, api="batched", transa=ta, transb=tb, m=m, n=n, k=k, alpha=3.0, beta=7.0, offset=off,
+                  batch=5)
+             for off, m, n, k, (ta, tb) in itertools.product([0, 33], [63, 128], [63, 128], [63, 128], TRANS)]
+    _run_all(handle, cases)
+
+
+@pytest.mark.parametrize("dt", ALL_DTYPES)
+def test_batched_beta_nonzero_ld_multiplied(handle, dt):
+    sizes = [63, 128, 129] if dt in ("f32", "f64") else [63, 129]
+    cases = [Case(dtype=dt, api="batched", transa=ta, transb=tb, m=m, n=n, k=k, alpha=3.0, beta=7.0, offset=off,
+                  batch=bs, batch_type=bt, lda_mul=2, ldb_mul=3, ldc_mul=4)
+             for off, bs, m, n, k, (ta, tb), bt in itertools.product([0, 33], [1, 5], sizes, sizes, sizes, TRANS,
+                                                                     [0, 1])]
+    _run_all(handle, cases)
+
+
+@pytest.mark.parametrize("dt", ALL_DTYPES)
+def test_batched_alpha_zero(handle, dt):
+    cases = [Case(dtype=dt, api="batched", transa=ta, transb=tb, m=128, n=128, k=128, alpha=0.0, beta=7.0, batch=5)
+             for ta, tb in TRANS]
+    cases += [Case(dtype=dt, api="batched", transa=ta, transb=tb, m=63, n=63, k=63, alpha=0.0, beta=7.0, batch=5,
+                   offset=off, lda_mul=2, ldb_mul=3, ldc_mul=4) for off, (ta, tb) in itertools.product([0, 33], TRANS)]
+    _run_all(handle, cases)
+
+
+@pytest.mark.parametrize("dt", ALL_DTYPES)
+def test_strided_batched_default(handle, dt):
+    cases = [Case(dtype=dt, api="strided", transa=ta, transb=tb, m=m, n=n, k=k, alpha=3.0, beta=7.0, offset=off,
+                  batch=bs)
+             for off, bs, m, n, k, (ta, tb) in itertools.product([0, 33], [1, 5], [63, 128], [63, 128], [63, 128],
+                                                                 TRANS)]
+    _run_all(handle, cases)
+
+
+@pytest.mark.parametrize("dt", ALL_DTYPES)
+def test_strided_batched_all_strides(handle, dt):
+    cases = [Case(dtype=dt, api="strided", transa=ta, transb=tb, m=63, n=63, k=128, alpha=al, beta=be, offset=off,
+                  batch=5, lda_mul=2, ldb_mul=3, ldc_mul=4, stride_a_mul=sa, stride_b_mul=sb, stride_c_mul=sc)
+             for off, (ta, tb), al, be, sa, sb, sc in itertools.product([0, 33], TRANS, [3.0, 0.0], [7.0, 1.0, 0.0],
+                                                                        [0, 1, 2], [0, 1, 2], [1, 3])]
+    _run_all(handle, cases)
+
+
+def test_strided_batched_tma_aligned(handle):
+    """Aligned batches (the cfg-4 shape family at reduced batch) must take the tcgen05 path,
+    including stride 0 broadcast of A or B."""
+    cases = []
+    for dt in ("f16", "bf16", "f16f32", "f32"):
+        for (ta, tb), sa, sb in itertools.product(TRANS, [0, 1], [0, 1]):
+            cases.append(Case(dtype=dt, api="strided", transa=ta, transb=tb, m=256, n=256, k=256, alpha=1.0, beta=0.0,
+                              batch=6, stride_a_mul=sa, stride_b_mul=sb, stride_c_mul=1))
+    _run_all(handle, cases)
+    assert run_case(handle, cases[0]).kernel == "tcgen05"
+
+
+# ---- invalid arguments (gemm_interface.hpp:144-165) ------------------------------------------------
+def test_invalid_arguments(handle):
+    cases = [Case(transa="x"), Case(transb="q"), Case(transa="c", transb="C"),
+             Case(api="strided", batch=3, stride_c_mul=0), Case(transa="x", alpha=0.0, beta=2.0)]
+    _run_all(handle, cases)
+
+
+# ---- TallSkinnyGemm suites (blas3_gemm_tall_skinny_test.cpp) + forced split-K ----------------------
+@pytest.mark.parametrize("dt", ["f32", "f64", "f16f32"])
+def test_tall_skinny(handle, dt):
+    cases = []
+    for off, m, n, k, (ta, tb), be, lds in itertools.product([0, 10], [7, 65], [9, 126], [2049, 1026], TRANS,
+                                                             [0.5, 0.0], [(1, 1, 1), (2, 3, 4)]):
+        cases.append(Case(dtype=dt, transa=ta, transb=tb, m=m, n=n, k=k, alpha=1.5, beta=be, offset=off,
+                          lda_mul=lds[0], ldb_mul=lds[1], ldc_mul=lds[2]))
+    _run_all(handle, cases)
+
+
+@pytest.mark.parametrize("dt,kernel", [("f32", TCGEN05), ("f32", SIMT), ("f64", DMMA), ("bf16f32", TCGEN05),
+                                       ("f16", TCGEN05)])
+def test_split_k_forced(handle, dt, kernel):
+    cases = [Case(dtype=dt, transa=ta, transb=tb, m=m, n=n, k=k, alpha=1.5, beta=be, kernel=kernel, split_k=sk)
+             for m, n, k, be, sk, (ta, tb) in itertools.product([72, 256], [136], [4104, 16384], [0.0, 0.5], [3, 7],
+                                                                TRANS)]
+    _run_all(handle, cases)
+    r = run_case(handle, cases[-1])
+    assert r.split_k == 7
+
+
+def test_split_k_auto_selected(handle):
+    """cfg-5 family at reduced K: M=N=512 gives 16 tiles on 148 SMs -> the selector must split K."""
+    r = run_case(handle, Case(dtype="f32", m=512, n=512, k=65536, alpha=1.0, beta=0.0))
+    assert r.ok, r
+    assert r.kernel == "tcgen05" and r.split_k > 1, r
+
+
+# ---- JointMatrix-style grid (test/unittest/joint_matrix/*.cpp): narrow-compute numerics ---------------
+@pytest.mark.parametrize("dt", ["f16f32", "bf16f32", "f16"])
+def test_joint_matrix_grid(handle, dt):
+    cases = []
+    for m, n, k in [(11, 11, 17), (33, 63, 64), (65, 127, 65), (255, 511, 127), (1024, 1535, 1536)]:
+        for (ta, tb), be in itertools.product(TRANS, [0.0, 1.5]):
+            cases.append(Case(dtype=dt, transa=ta, transb=tb, m=m, n=n, k=k, alpha=1.5, beta=be, offset=33))
+    _run_all(handle, cases)
