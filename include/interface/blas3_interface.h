@@ -1,0 +1,151 @@
+// interface/blas3_interface.h -- blas::_gemm / _gemm_batched / _gemm_strided_batched.
+//
+// Same templates, argument order and defaults as reference
+// include/interface/blas3_interface.h:86-123.  internal::_gemm* restate the front end of
+// src/interface/gemm_interface.hpp:189-240 (default strides for _gemm_batched :213-219) and then
+// cross the drop-in boundary: one extern "C" call (pbx_gemm, include/pbx_gemm.h) on the queue's
+// CUDA stream instead of backend::_gemm -> Gemm_Launcher::_select_gemm -> sb_handle.execute.
+// The remaining front-end rules (alpha==0 shortcut, trans / stride validation, beta==0
+// specialisation) live behind the C-ABI so every binding shares them; invalid arguments come
+// back as status codes and are rethrown here as the reference's std::invalid_argument texts.
+#pragma once
+#include <cuda_bf16.h>
+
+#include <cctype>
+#include <iostream>
+#include <stdexcept>
+#include <type_traits>
+
+#include "../blas_meta.h"
+#include "../container/sycl_iterator.h"
+#include "../operations/blas3_trees.h"
+#include "../sb_handle/portblas_handle.h"
+
+namespace blas {
+namespace internal {
+
+template <typename in_t, typename out_t> struct pbx_dtype_of;
+template <> struct pbx_dtype_of<float, float> { static constexpr int value = PBX_F32; };
+template <> struct pbx_dtype_of<double, double> { static constexpr int value = PBX_F64; };
+template <> struct pbx_dtype_of<sycl::half, sycl::half> { static constexpr int value = PBX_F16; };
+template <> struct pbx_dtype_of<sycl::half, float> { static constexpr int value = PBX_F16_F32; };
+template <> struct pbx_dtype_of<__nv_bfloat16, __nv_bfloat16> { static constexpr int value = PBX_BF16; };
+template <> struct pbx_dtype_of<__nv_bfloat16, float> { static constexpr int value = PBX_BF16_F32; };
+
+inline void throw_on_status(pbx_handle_t h, int st) {
+  if (st == PBX_OK) return;
+  if (st >= PBX_ERR_INVALID_TRANSA && st <= PBX_ERR_INVALID_STRIDEB)
+    throw std::invalid_argument(pbx_status_string(st));  // gemm_interface.hpp:144-165
+  std::string msg = std::string(pbx_status_string(st)) + ": " + pbx_last_error(h);
+  std::cerr << "[portblas-b200] " << msg << std::endl;  // reference prints sycl::exception text (kernel_constructor.hpp:213-216)
+  throw std::runtime_error(msg);
+}
+
+template <typename sb_handle_t, typename container_0_t, typename container_1_t, typename container_2_t,
+          typename element_t, typename index_t>
+typename sb_handle_t::event_t _gemm_backend(sb_handle_t& sb_handle, char _TransA, char _TransB, index_t _M,
+                                            index_t _N, index_t _K, element_t _alpha, container_0_t a_,
+                                            index_t _lda, index_t _stridea, container_1_t b_, index_t _ldb,
+                                            index_t _strideb, element_t _beta, container_2_t _C, index_t _ldc,
+                                            index_t _stridec, index_t batch_size, gemm_batch_type_t batch_type,
+                                            const typename sb_handle_t::event_t& _dependencies) {
+  using in_t = typename ValueType<container_0_t>::type;
+  using in1_t = typename ValueType<container_1_t>::type;
+  using out_t = typename ValueType<container_2_t>::type;
+  static_assert(std::is_same_v<in_t, in1_t>, "A and B must share an element type");
+  constexpr int dtype = pbx_dtype_of<in_t, out_t>::value;
+  // scalars cross the C-ABI as double (fp64) or float (everything else)
+  using scalar_abi_t = std::conditional_t<std::is_same_v<out_t, double>, double, float>;
+  const scalar_abi_t alpha = static_cast<scalar_abi_t>(_alpha);
+  const scalar_abi_t beta = static_cast<scalar_abi_t>(_beta);
+  auto q = sb_handle.get_queue();
+  sycl::event ev = q.submit([&](sycl::handler& cgh) {
+    cgh.depends_on(_dependencies);
+    const int st = pbx_gemm(cgh.pbx(), dtype, _TransA, _TransB, static_cast<int64_t>(_M), static_cast<int64_t>(_N),
+                            static_cast<int64_t>(_K), &alpha, get_device_ptr(a_), static_cast<int64_t>(_lda),
+                            static_cast<int64_t>(_stridea), get_device_ptr(b_), static_cast<int64_t>(_ldb),
+                            static_cast<int64_t>(_strideb), &beta,
+                            const_cast<std::remove_const_t<out_t>*>(get_device_ptr(_C)), static_cast<int64_t>(_ldc),
+                            static_cast<int64_t>(_stridec), static_cast<int64_t>(batch_size),
+                            static_cast<int>(batch_type));
+    throw_on_status(cgh.pbx(), st);
+  });
+  return typename sb_handle_t::event_t{ev};
+}
+
+template <typename sb_handle_t, typename container_0_t, typename container_1_t, typename container_2_t,
+          typename element_t, typename index_t>
+typename sb_handle_t::event_t _gemm(sb_handle_t& sb_handle, char _TransA, char _TransB, index_t _M, index_t _N,
+                                    index_t _K, element_t _alpha, container_0_t a_, index_t _lda, container_1_t b_,
+                                    index_t _ldb, element_t _beta, container_2_t _C, index_t _ldc,
+                                    const typename sb_handle_t::event_t& _dependencies) {
+  return _gemm_backend(sb_handle, _TransA, _TransB, _M, _N, _K, _alpha, a_, _lda, index_t(0), b_, _ldb, index_t(0),
+                       _beta, _C, _ldc, index_t(0), index_t(1), gemm_batch_type_t::strided, _dependencies);
+}
+
+template <typename sb_handle_t, typename container_0_t, typename container_1_t, typename container_2_t,
+          typename element_t, typename index_t>
+typename sb_handle_t::event_t _gemm_batched(sb_handle_t& sb_handle, char _TransA, char _TransB, index_t _M,
+                                            index_t _N, index_t _K, element_t _alpha, container_0_t a_, index_t _lda,
+                                            container_1_t b_, index_t _ldb, element_t _beta, container_2_t _C,
+                                            index_t _ldc, index_t batch_size, gemm_batch_type_t batch_type,
+                                            const typename sb_handle_t::event_t& _dependencies) {
+  index_t _stridea = 0, _strideb = 0, _stridec = 0;
+  if (batch_type == gemm_batch_type_t::strided) {  // matrix footprints (gemm_interface.hpp:213-219)
+    _stridea = (std::tolower(_TransA) != 'n') ? _M * _lda : _K * _lda;
+    _strideb = (std::tolower(_TransB) != 'n') ? _ldb * _K : _N * _ldb;
+    _stridec = _ldc * _N;
+  }
+  return _gemm_backend(sb_handle, _TransA, _TransB, _M, _N, _K, _alpha, a_, _lda, _stridea, b_, _ldb, _strideb,
+                       _beta, _C, _ldc, _stridec, batch_size, batch_type, _dependencies);
+}
+
+template <typename sb_handle_t, typename container_0_t, typename container_1_t, typename container_2_t,
+          typename element_t, typename index_t>
+typename sb_handle_t::event_t _gemm_strided_batched(sb_handle_t& sb_handle, char _TransA, char _TransB, index_t _M,
+                                                    index_t _N, index_t _K, element_t _alpha, container_0_t a_,
+                                                    index_t _lda, index_t _stridea, container_1_t b_, index_t _ldb,
+                                                    index_t _strideb, element_t _beta, container_2_t _C,
+                                                    index_t _ldc, index_t _stridec, index_t batch_size,
+                                                    const typename sb_handle_t::event_t& _dependencies) {
+  return _gemm_backend(sb_handle, _TransA, _TransB, _M, _N, _K, _alpha, a_, _lda, _stridea, b_, _ldb, _strideb,
+                       _beta, _C, _ldc, _stridec, batch_size, gemm_batch_type_t::strided, _dependencies);
+}
+
+}  // namespace internal
+
+template <typename sb_handle_t, typename container_0_t, typename container_1_t, typename container_2_t,
+          typename element_t, typename index_t>
+typename sb_handle_t::event_t _gemm(sb_handle_t& sb_handle, char _TransA, char _TransB, index_t _M, index_t _N,
+                                    index_t _K, element_t _alpha, container_0_t a_, index_t _lda, container_1_t b_,
+                                    index_t _ldb, element_t _beta, container_2_t _C, index_t _ldc,
+                                    const typename sb_handle_t::event_t& _dependencies = {}) {
+  return internal::_gemm(sb_handle, _TransA, _TransB, _M, _N, _K, _alpha, a_, _lda, b_, _ldb, _beta, _C, _ldc,
+                         _dependencies);
+}
+
+template <typename sb_handle_t, typename container_0_t, typename container_1_t, typename container_2_t,
+          typename element_t, typename index_t>
+typename sb_handle_t::event_t _gemm_batched(sb_handle_t& sb_handle, char _TransA, char _TransB, index_t _M,
+                                            index_t _N, index_t _K, element_t _alpha, container_0_t a_, index_t _lda,
+                                            container_1_t b_, index_t _ldb, element_t _beta, container_2_t _C,
+                                            index_t _ldc, index_t batch_size,
+                                            gemm_batch_type_t batch_type = gemm_batch_type_t::strided,
+                                            const typename sb_handle_t::event_t& _dependencies = {}) {
+  return internal::_gemm_batched(sb_handle, _TransA, _TransB, _M, _N, _K, _alpha, a_, _lda, b_, _ldb, _beta, _C,
+                                 _ldc, batch_size, batch_type, _dependencies);
+}
+
+template <typename sb_handle_t, typename container_0_t, typename container_1_t, typename container_2_t,
+          typename element_t, typename index_t>
+typename sb_handle_t::event_t _gemm_strided_batched(sb_handle_t& sb_handle, char _TransA, char _TransB, index_t _M,
+                                                    index_t _N, index_t _K, element_t _alpha, container_0_t a_,
+                                                    index_t _lda, index_t _stridea, container_1_t b_, index_t _ldb,
+                                                    index_t _strideb, element_t _beta, container_2_t _C,
+                                                    index_t _ldc, index_t _stridec, index_t batch_size,
+                                                    const typename sb_handle_t::event_t& _dependencies = {}) {
+  return internal::_gemm_strided_batched(sb_handle, _TransA, _TransB, _M, _N, _K, _alpha, a_, _lda, _stridea, b_,
+                                         _ldb, _strideb, _beta, _C, _ldc, _stridec, batch_size, _dependencies);
+}
+
+}  // namespace blas

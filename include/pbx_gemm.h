@@ -178,6 +178,21 @@ int pbx_copy_to_device(pbx_handle_t h, const void* host_src, void* dev_dst, int6
 int pbx_copy_to_host(pbx_handle_t h, const void* dev_src, void* host_dst, int64_t bytes);
 int pbx_fill_bytes(pbx_handle_t h, void* dev_dst, int value, int64_t bytes);
 
+int pbx_copy_device_to_device(pbx_handle_t h, const void* dev_src, void* dev_dst, int64_t bytes);
+/* typed fill: `count` elements of `elem_bytes` (2, 4 or 8) bytes each set to *value */
+int pbx_fill(pbx_handle_t h, void* dev_dst, const void* value, int elem_bytes, int64_t count);
+
+/* ---- events (what the reference returns from every call: sb_handle_t::event_t =
+ * std::vector<sycl::event>, include/sb_handle/portblas_handle.h:48; profiling as in
+ * benchmark/portblas/utils.hpp:52-63) ---------------------------------------------------- */
+int pbx_event_create(pbx_handle_t h, void** event_out);
+int pbx_event_record(pbx_handle_t h, void* event);          /* on the handle's stream */
+int pbx_event_synchronize(pbx_handle_t h, void* event);     /* sycl::event::wait() */
+int pbx_event_elapsed_ms(pbx_handle_t h, void* start, void* end, float* ms_out);
+int pbx_event_destroy(pbx_handle_t h, void* event);
+int pbx_stream_wait_event(pbx_handle_t h, void* event);     /* handler::depends_on() */
+int pbx_device_name(pbx_handle_t h, char* buf, int len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,11 @@
+// portblas.h -- umbrella header of the B200 GEMM path (reference include/portblas.h:25-66).
+// Only the GEMM-path headers exist in this build; BLAS-1/2, symm/trsm and the extension
+// operators of the reference are out of scope.
+#pragma once
+#include "blas_meta.h"
+#include "container/sycl_iterator.h"
+#include "interface/blas3_interface.h"
+#include "operations/blas3_trees.h"
+#include "portblas_helper.h"
+#include "sb_handle/portblas_handle.h"
+#include "views/view.h"

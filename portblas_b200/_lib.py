@@ -51,6 +51,15 @@ SYMBOLS = {
     "pbx_copy_to_device": (c_int, [c_void_p, c_void_p, c_void_p, c_int64]),
     "pbx_copy_to_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64]),
     "pbx_fill_bytes": (c_int, [c_void_p, c_void_p, c_int, c_int64]),
+    "pbx_copy_device_to_device": (c_int, [c_void_p, c_void_p, c_void_p, c_int64]),
+    "pbx_fill": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64]),
+    "pbx_event_create": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "pbx_event_record": (c_int, [c_void_p, c_void_p]),
+    "pbx_event_synchronize": (c_int, [c_void_p, c_void_p]),
+    "pbx_event_elapsed_ms": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(ctypes.c_float)]),
+    "pbx_event_destroy": (c_int, [c_void_p, c_void_p]),
+    "pbx_stream_wait_event": (c_int, [c_void_p, c_void_p]),
+    "pbx_device_name": (c_int, [c_void_p, c_char_p, c_int]),
 }
 
 _lib = None

@@ -23,6 +23,11 @@
 //
 // fp32 (3xTF32): a = hi + lo with hi = tf32(a), lo = tf32(a - hi);
 //   D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi   (fp32 accumulate, lo*lo dropped: ~2^-22 relative)
+// The tensor core adds into its fp32 accumulator with truncation, a one-sided error that grows
+// linearly with the length of the accumulation chain (measured: ~7e-9 relative per k).  To keep
+// fp32 results within ~1e-5 the K loop is cut into chunks of kb_per_chunk blocks; each chunk
+// starts a fresh TMEM accumulator and the epilogue warps fold finished chunks into a running sum
+// (a third TMEM region) with round-to-nearest CUDA-core adds while the next chunk is in flight.
 #include <stdio.h>
 
 #include <mutex>
@@ -43,6 +48,7 @@ struct TcParams {
   float alpha, beta;
   int batch, slices, m_tiles, n_tiles, group_m;
   int kb_total, kb_per_slice;
+  int kb_per_chunk;  // K blocks accumulated inside the tensor core before an fp32 RN add (see below)
   int a_batched, b_batched;
   int64_t total_tiles;
 };
@@ -75,7 +81,9 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = RAW_BYTES * (TF32X3 ? 2 : 1);  // + lo copies
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + align slack
-  static constexpr int TMEM_COLS = 2 * BN;         // 256 or 512 (powers of two)
+  // two MMA accumulator stages; fp32 adds a running-sum region (3*128 = 384 -> 512 columns)
+  static constexpr int TMEM_COLS = TF32X3 ? 512 : 2 * BN;
+  static constexpr int RSUM_COL = 2 * BN;          // running sum of chunk partials (fp32 only)
   static constexpr int NUM_THREADS = TF32X3 ? 384 : 256;
   static constexpr int NUM_SPLIT_THREADS = 128;
 };
@@ -199,40 +207,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t A_SBO = (TF32X3 && A_MN) ? 512u : 1024u, B_SBO = (TF32X3 && B_MN) ? 512u : 1024u;
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      int it = 0;  // accumulator hand-offs so far (one per K chunk)
+      for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
         const int kb0 = tc.slice * p.kb_per_slice;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_slice);
-        const int as = it & 1;
-        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-        mbar_wait(tempty_bar(as), aphase ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(TF32X3 ? split_bar(stage) : full_bar(stage), phase);
+        for (int kc0 = kb0; kc0 < kb1; kc0 += p.kb_per_chunk, ++it) {
+          const int kc1 = min(kb1, kc0 + p.kb_per_chunk);
+          const int as = it & 1;
+          const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+          mbar_wait(tempty_bar(as), aphase ^ 1u);
           tc_fence_after();
-          const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
-          const uint32_t sB = sA + Cfg::A_BYTES;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+          for (int kb = kc0; kb < kc1; ++kb) {
+            mbar_wait(TF32X3 ? split_bar(stage) : full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
+            const uint32_t sB = sA + Cfg::A_BYTES;
 #pragma unroll
-          for (int k = 0; k < BK / Cfg::UMMA_K; ++k) {
-            const uint64_t adesc = make_smem_desc(sA + k * A_KSTEP, A_LBO, A_SBO, A_LT);
-            const uint64_t bdesc = make_smem_desc(sB + k * B_KSTEP, B_LBO, B_SBO, B_LT);
-            const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
-            if (TF32X3) {
-              const uint64_t adesc_lo = make_smem_desc(sA + Cfg::RAW_BYTES + k * A_KSTEP, A_LBO, A_SBO, A_LT);
-              const uint64_t bdesc_lo = make_smem_desc(sB + Cfg::RAW_BYTES + k * B_KSTEP, B_LBO, B_SBO, B_LT);
-              tc_mma<true>(d_tmem, adesc_lo, bdesc, idesc, acc);
-              tc_mma<true>(d_tmem, adesc, bdesc_lo, idesc, 1u);
-              tc_mma<true>(d_tmem, adesc, bdesc, idesc, 1u);
-            } else {
-              tc_mma<false>(d_tmem, adesc, bdesc, idesc, acc);
+            for (int k = 0; k < BK / Cfg::UMMA_K; ++k) {
+              const uint64_t adesc = make_smem_desc(sA + k * A_KSTEP, A_LBO, A_SBO, A_LT);
+              const uint64_t bdesc = make_smem_desc(sB + k * B_KSTEP, B_LBO, B_SBO, B_LT);
+              const uint32_t acc = (kb > kc0 || k > 0) ? 1u : 0u;
+              if (TF32X3) {
+                const uint64_t adesc_lo = make_smem_desc(sA + Cfg::RAW_BYTES + k * A_KSTEP, A_LBO, A_SBO, A_LT);
+                const uint64_t bdesc_lo = make_smem_desc(sB + Cfg::RAW_BYTES + k * B_KSTEP, B_LBO, B_SBO, B_LT);
+                tc_mma<true>(d_tmem, adesc_lo, bdesc, idesc, acc);
+                tc_mma<true>(d_tmem, adesc, bdesc_lo, idesc, 1u);
+                tc_mma<true>(d_tmem, adesc, bdesc, idesc, 1u);
+              } else {
+                tc_mma<false>(d_tmem, adesc, bdesc, idesc, acc);
+              }
             }
+            tc_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
-          tc_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          tc_commit(tfull_bar(as));  // chunk accumulator complete
         }
-        tc_commit(tfull_bar(as));  // accumulator complete
       }
     }
     __syncwarp();
@@ -241,46 +252,66 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ew = warp & 3;  // TMEM lane quarter this warp may read
     const bool beta0 = (p.beta == 0.0f);
     int it = 0;
-    for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
-      const int as = it & 1;
-      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(tfull_bar(as), aphase);
-      tc_fence_after();
+      const int kb0 = tc.slice * p.kb_per_slice;
+      const int kb1 = min(p.kb_total, kb0 + p.kb_per_slice);
       const int64_t m = (int64_t)tc.mt * BM + ew * 32 + lane;
       const int64_t n0 = (int64_t)tc.nt * BN;
       const bool m_ok = m < p.M;
-      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
+      for (int kc0 = kb0; kc0 < kb1; kc0 += p.kb_per_chunk, ++it) {
+        const bool first = (kc0 == kb0), last = (kc0 + p.kb_per_chunk >= kb1);
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tfull_bar(as), aphase);
+        tc_fence_after();
+        const uint32_t t_lane = tmem_base + ((uint32_t)(ew * 32) << 16);
+        const uint32_t t_row = t_lane + (uint32_t)(as * BN);
+        const uint32_t t_sum = t_lane + (uint32_t)Cfg::RSUM_COL;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (n0 + c0 >= p.N) break;  // warp-uniform
-        uint32_t v[32];
-        tmem_ld_32x32(t_row + c0, v);
-        tmem_ld_wait();
-        if (p.slices > 1) {
-          float* ws = p.ws + (((int64_t)tc.b * p.slices + tc.slice) * p.N) * p.M;
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          if (n0 + c0 >= p.N) break;  // warp-uniform
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + c0, v);
+          if (TF32X3 && !first) {
+            uint32_t r[32];
+            tmem_ld_32x32(t_sum + c0, r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int64_t n = n0 + c0 + j;
-            if (m_ok && n < p.N) ws[n * p.M + m] = __uint_as_float(v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(r[j]));
+          } else {
+            tmem_ld_wait();
           }
-        } else {
-          TOut* C = reinterpret_cast<TOut*>(p.C) + (int64_t)tc.b * p.sc;
+          if (TF32X3 && !last) {
+            tmem_st_32x32(t_sum + c0, v);
+            continue;
+          }
+          if (p.slices > 1) {
+            float* ws = p.ws + (((int64_t)tc.b * p.slices + tc.slice) * p.N) * p.M;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int64_t n = n0 + c0 + j;
-            if (m_ok && n < p.N) {
-              TOut* dst = C + m + n * p.ldc;
-              float r = p.alpha * __uint_as_float(v[j]);
-              if (!beta0) r += p.beta * OutCvt<TOut>::load(dst);
-              OutCvt<TOut>::store(dst, r);
+            for (int j = 0; j < 32; ++j) {
+              const int64_t n = n0 + c0 + j;
+              if (m_ok && n < p.N) ws[n * p.M + m] = __uint_as_float(v[j]);
+            }
+          } else {
+            TOut* C = reinterpret_cast<TOut*>(p.C) + (int64_t)tc.b * p.sc;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int64_t n = n0 + c0 + j;
+              if (m_ok && n < p.N) {
+                TOut* dst = C + m + n * p.ldc;
+                float r = p.alpha * __uint_as_float(v[j]);
+                if (!beta0) r += p.beta * OutCvt<TOut>::load(dst);
+                OutCvt<TOut>::store(dst, r);
+              }
             }
           }
         }
+        if (TF32X3 && !last) tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
     }
   } else if (TF32X3 && warp >= 8) {
     // ===================== fp32 -> (hi, lo) tf32 splitters =====================
@@ -433,6 +464,8 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
   p.group_m = 8;
   p.kb_total = (int)((c.k + bk - 1) / bk);
   p.kb_per_slice = (p.kb_total + slices - 1) / slices;
+  // fp32: 16 blocks x 32 = 512 k per tensor-core accumulation chain (~4e-6 relative bias per chunk)
+  p.kb_per_chunk = f32 ? 16 : (1 << 30);
   p.a_batched = (c.batch > 1 && c.sa > 0) ? 1 : 0;
   p.b_batched = (c.batch > 1 && c.sb > 0) ? 1 : 0;
   p.total_tiles = (int64_t)p.m_tiles * p.n_tiles * c.batch * slices;

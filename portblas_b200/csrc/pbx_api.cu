@@ -309,6 +309,77 @@ int pbx_fill_bytes(pbx_handle_t h, void* dst, int value, int64_t bytes) {
   return PBX_OK;
 }
 
+int pbx_copy_device_to_device(pbx_handle_t h, const void* src, void* dst, int64_t bytes) {
+  if (!h || bytes < 0) return PBX_ERR_INVALID_ARG;
+  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  PBX_CUDA_CHECK(h, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, h->stream));
+  return PBX_OK;
+}
+
+}  // extern "C"
+template <typename T>
+__global__ void pbx_fill_kernel(T* dst, T v, int64_t count) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = v;
+}
+extern "C" {
+
+int pbx_fill(pbx_handle_t h, void* dst, const void* value, int elem_bytes, int64_t count) {
+  if (!h || !value || count < 0 || (elem_bytes != 2 && elem_bytes != 4 && elem_bytes != 8)) return PBX_ERR_INVALID_ARG;
+  if (count == 0) return PBX_OK;
+  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  int64_t blocks = (count + 255) / 256;
+  if (blocks > (int64_t)h->sm_count * 16) blocks = (int64_t)h->sm_count * 16;
+  if (elem_bytes == 2) pbx_fill_kernel<uint16_t><<<(unsigned)blocks, 256, 0, h->stream>>>((uint16_t*)dst, *(const uint16_t*)value, count);
+  else if (elem_bytes == 4) pbx_fill_kernel<uint32_t><<<(unsigned)blocks, 256, 0, h->stream>>>((uint32_t*)dst, *(const uint32_t*)value, count);
+  else pbx_fill_kernel<uint64_t><<<(unsigned)blocks, 256, 0, h->stream>>>((uint64_t*)dst, *(const uint64_t*)value, count);
+  h->launches++;
+  PBX_CUDA_CHECK(h, cudaGetLastError());
+  return PBX_OK;
+}
+
+// ---- events ---------------------------------------------------------------------------------
+int pbx_event_create(pbx_handle_t h, void** ev) {
+  if (!h || !ev) return PBX_ERR_INVALID_ARG;
+  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  cudaEvent_t e;
+  PBX_CUDA_CHECK(h, cudaEventCreate(&e));
+  *ev = (void*)e;
+  return PBX_OK;
+}
+int pbx_event_record(pbx_handle_t h, void* ev) {
+  if (!h || !ev) return PBX_ERR_INVALID_ARG;
+  PBX_CUDA_CHECK(h, cudaEventRecord((cudaEvent_t)ev, h->stream));
+  return PBX_OK;
+}
+int pbx_event_synchronize(pbx_handle_t h, void* ev) {
+  if (!h || !ev) return PBX_ERR_INVALID_ARG;
+  PBX_CUDA_CHECK(h, cudaEventSynchronize((cudaEvent_t)ev));
+  return PBX_OK;
+}
+int pbx_event_elapsed_ms(pbx_handle_t h, void* a, void* b, float* ms) {
+  if (!h || !a || !b || !ms) return PBX_ERR_INVALID_ARG;
+  PBX_CUDA_CHECK(h, cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b));
+  return PBX_OK;
+}
+int pbx_event_destroy(pbx_handle_t h, void* ev) {
+  if (!h || !ev) return PBX_ERR_INVALID_ARG;
+  PBX_CUDA_CHECK(h, cudaEventDestroy((cudaEvent_t)ev));
+  return PBX_OK;
+}
+int pbx_stream_wait_event(pbx_handle_t h, void* ev) {
+  if (!h || !ev) return PBX_ERR_INVALID_ARG;
+  PBX_CUDA_CHECK(h, cudaStreamWaitEvent(h->stream, (cudaEvent_t)ev, 0));
+  return PBX_OK;
+}
+int pbx_device_name(pbx_handle_t h, char* buf, int len) {
+  if (!h || !buf || len <= 0) return PBX_ERR_INVALID_ARG;
+  cudaDeviceProp prop;
+  PBX_CUDA_CHECK(h, cudaGetDeviceProperties(&prop, h->device));
+  snprintf(buf, (size_t)len, "%s", prop.name);
+  return PBX_OK;
+}
+
 // ---- host-buffer path (end-to-end metric) ------------------------------------------------
 static int ensure_stage(pbx_handle_t h, int i, int64_t bytes) {
   if (bytes <= h->stage_bytes[i]) return PBX_OK;
