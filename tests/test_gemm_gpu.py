@@ -205,3 +205,35 @@ def test_joint_matrix_grid(handle, dt):
         for (ta, tb), be in itertools.product(TRANS, [0.0, 1.5]):
             cases.append(Case(dtype=dt, transa=ta, transb=tb, m=m, n=n, k=k, alpha=1.5, beta=be, offset=33))
     _run_all(handle, cases)
+
+
+# ---- committed golden vectors (tests/golden/make_golden.py) through the CUDA path ----------------------
+def test_golden_fixtures_gpu(handle):
+    from pathlib import Path
+
+    import numpy as np
+    import torch
+
+    from oracle import oracle
+    from portblas_b200 import blas
+
+    g = np.load(Path(__file__).parent / "golden" / "gemm_golden.npz", allow_pickle=False)
+    n_cases = len([k for k in g.files if k.endswith("_meta")])
+    tmap = {"f32": (torch.float32, "float"), "f64": (torch.float64, "double"), "f16": (torch.float16, "half"),
+            "bf16": (torch.bfloat16, "half")}
+    for i in range(n_cases):
+        dt, ta, tb, m, n, k, al, be, la, lb, lc, batch = g[f"case{i}_meta"]
+        m, n, k, la, lb, lc, batch = (int(x) for x in (m, n, k, la, lb, lc, batch))
+        tdt, kind = tmap[str(dt)]
+        lda, ldb, ldc = (k if ta == "t" else m) * la, (n if tb == "t" else k) * lb, m * lc
+        a = torch.from_numpy(g[f"case{i}_A"]).cuda().to(tdt)
+        b = torch.from_numpy(g[f"case{i}_B"]).cuda().to(tdt)
+        c = torch.from_numpy(g[f"case{i}_C"]).cuda().to(tdt)
+        if batch == 1:
+            blas._gemm(handle, str(ta), str(tb), m, n, k, float(al), a, lda, b, ldb, float(be), c, ldc)
+        else:
+            blas._gemm_strided_batched(handle, str(ta), str(tb), m, n, k, float(al), a, lda, m * k * la, b, ldb,
+                                       k * n * lb, float(be), c, ldc, m * n * lc, batch)
+        handle.wait()
+        got = c.to(torch.float64 if dt == "f64" else torch.float32).cpu().numpy()
+        assert oracle.compare(got, g[f"case{i}_out"], kind) == 0, f"golden case {i} ({dt} {ta}{tb} {m}x{n}x{k})"
