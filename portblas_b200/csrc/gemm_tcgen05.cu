@@ -49,6 +49,7 @@ struct TcParams {
   int batch, slices, m_tiles, n_tiles, group_m;
   int kb_total, kb_per_slice;
   int kb_per_chunk;  // K blocks accumulated inside the tensor core before an fp32 RN add (see below)
+  int raw_hi;        // fp32: 1 = feed raw fp32 as the hi operand (hardware truncates to tf32)
   int a_batched, b_batched;
   int64_t total_tiles;
 };
@@ -67,25 +68,34 @@ template <> struct OutCvt<__nv_bfloat16> {
   __device__ static void store(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 };
 
-constexpr int BM = 128;
+constexpr int BM = 128;         // rows of D held by one CTA (TMEM lanes)
 constexpr int ROW_BYTES = 128;  // one swizzle row
 
-template <int ES, int BN, int STAGES>
+// CG = 1: one CTA computes a 128 x BN tile.  CG = 2: a CTA pair (2-CTA cluster, cta_group::2)
+// computes a 256 x BN tile; each CTA stages its own 128 rows of A and BN/2 rows of B, so the
+// shared-memory read rate per SM halves for the same MMA rate.
+template <int ES, int BN, int STAGES, int CG>
 struct TcCfg {
   static constexpr bool TF32X3 = (ES == 4);
   static constexpr int BK = ROW_BYTES / ES;        // 64 (16-bit) or 32 (fp32) elements
   static constexpr int UMMA_K = 32 / ES;           // 16 or 8
+  static constexpr int TILE_M = BM * CG;
+  static constexpr int BN_CTA = BN / CG;           // rows of the B operand staged by this CTA
   static constexpr int A_BYTES = BM * ROW_BYTES;   // 16 KiB
-  static constexpr int B_BYTES = BN * ROW_BYTES;
+  static constexpr int B_BYTES = BN_CTA * ROW_BYTES;
   static constexpr int RAW_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGE_BYTES = RAW_BYTES * (TF32X3 ? 2 : 1);  // + lo copies
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + align slack
-  // two MMA accumulator stages; fp32 adds a running-sum region (3*128 = 384 -> 512 columns)
+  // TMEM: ACC_STAGES accumulators of BN columns (+ for fp32 a BN-column running sum)
+  static constexpr int ACC_STAGES = TF32X3 ? ((3 * BN <= 512) ? 2 : 1) : 2;
+  static constexpr int RSUM_COL = ACC_STAGES * BN;
   static constexpr int TMEM_COLS = TF32X3 ? 512 : 2 * BN;
-  static constexpr int RSUM_COL = 2 * BN;          // running sum of chunk partials (fp32 only)
-  static constexpr int NUM_THREADS = TF32X3 ? 384 : 256;
-  static constexpr int NUM_SPLIT_THREADS = 128;
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int SPLIT_WARPS = TF32X3 ? 4 : 0;
+  static constexpr int NUM_THREADS = 32 * (4 + EPI_WARPS + SPLIT_WARPS);
+  static constexpr int NUM_SPLIT_THREADS = 32 * SPLIT_WARPS;
+  static_assert(BN % (32 * 2) == 0 && BN <= 256 && (BN_CTA % 8) == 0, "tile width");
 };
 
 struct TileCoord {
@@ -108,13 +118,14 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int64_t tile
   return c;
 }
 
-template <typename TIn, typename TOut, int BN, int STAGES, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(TcCfg<sizeof(TIn), BN, STAGES>::NUM_THREADS, 1)
+template <typename TIn, typename TOut, int BN, int STAGES, bool A_MN, bool B_MN, int CG>
+__global__ void __launch_bounds__(TcCfg<sizeof(TIn), BN, STAGES, CG>::NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcParams p) {
-  using Cfg = TcCfg<sizeof(TIn), BN, STAGES>;
+  using Cfg = TcCfg<sizeof(TIn), BN, STAGES, CG>;
   constexpr bool TF32X3 = Cfg::TF32X3;
   constexpr int BK = Cfg::BK;
+  constexpr int ACC_STAGES = Cfg::ACC_STAGES;
   constexpr uint32_t FMT = TF32X3 ? 2u : (std::is_same<TIn, __nv_bfloat16>::value ? 1u : 0u);
 
   extern __shared__ uint8_t smem_raw[];
@@ -132,6 +143,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs)
+  const int64_t group = blockIdx.x / CG, num_groups = gridDim.x / CG;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -141,31 +154,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
-      mbar_init(split_bar(s), Cfg::NUM_SPLIT_THREADS);
+      mbar_init(split_bar(s), CG * Cfg::NUM_SPLIT_THREADS + (TF32X3 ? 0 : 1));
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);
+      mbar_init(tempty_bar(s), CG * Cfg::EPI_WARPS);
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if (CG == 2) { tmem_alloc_2sm(tmem_ptr_smem, Cfg::TMEM_COLS); tmem_relinquish_2sm(); }
+    else { tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // peer barriers must exist before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_generic;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA loads its own A rows and B rows) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      // 16-bit pair mode: both CTAs credit the leader's full barrier (the MMA issuer waits there).
+      // fp32 pair mode: each CTA's splitter warps wait on their OWN full barrier.
+      constexpr bool kLeaderFull = (CG == 2) && !TF32X3;
+      for (int64_t tile = group; tile < p.total_tiles; tile += num_groups) {
         const TileCoord tc = decode_tile(p, tile);
-        const int m0 = tc.mt * BM, n0 = tc.nt * BN;
+        const int m0 = tc.mt * Cfg::TILE_M + (int)rank * BM;
+        const int n0 = tc.nt * BN + (int)rank * Cfg::BN_CTA;
         const int kb0 = tc.slice * p.kb_per_slice;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_slice);
         const int za = p.a_batched ? tc.b : 0, zb = p.b_batched ? tc.b : 0;
@@ -173,20 +190,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sB = sA + Cfg::A_BYTES;
-          mbar_expect_tx(full_bar(stage), Cfg::RAW_BYTES);
+          const uint32_t fb = full_bar(stage);
+          if (kLeaderFull) { if (rank == 0) mbar_expect_tx(fb, 2 * Cfg::RAW_BYTES); }
+          else mbar_expect_tx(fb, Cfg::RAW_BYTES);
+          auto load = [&](uint32_t dst, const CUtensorMap* tm, int x, int y, int z) {
+            if (kLeaderFull) tma_load_3d_2sm(dst, tm, fb, x, y, z);
+            else tma_load_3d(dst, tm, fb, x, y, z);
+          };
           if (A_MN) {
 #pragma unroll
-            for (int c = 0; c < BM / BK; ++c)
-              tma_load_3d(sA + c * BK * ROW_BYTES, &tmA, full_bar(stage), m0 + c * BK, kb * BK, za);
+            for (int c = 0; c < BM / BK; ++c) load(sA + c * BK * ROW_BYTES, &tmA, m0 + c * BK, kb * BK, za);
           } else {
-            tma_load_3d(sA, &tmA, full_bar(stage), kb * BK, m0, za);
+            load(sA, &tmA, kb * BK, m0, za);
           }
           if (B_MN) {
 #pragma unroll
-            for (int c = 0; c < BN / BK; ++c)
-              tma_load_3d(sB + c * BK * ROW_BYTES, &tmB, full_bar(stage), n0 + c * BK, kb * BK, zb);
+            for (int c = 0; c < Cfg::BN_CTA / BK; ++c) load(sB + c * BK * ROW_BYTES, &tmB, n0 + c * BK, kb * BK, zb);
           } else {
-            tma_load_3d(sB, &tmB, full_bar(stage), kb * BK, n0, zb);
+            load(sB, &tmB, kb * BK, n0, zb);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -194,9 +215,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(FMT, A_MN, B_MN, BN);
+    // ===================== MMA issuer (one lane; leader CTA only in pair mode) =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc(FMT, A_MN, B_MN, BN, Cfg::TILE_M);
       // byte advance of the descriptor start address per UMMA_K step
       constexpr uint32_t A_KSTEP = A_MN ? Cfg::UMMA_K * ROW_BYTES : 32;
       constexpr uint32_t B_KSTEP = B_MN ? Cfg::UMMA_K * ROW_BYTES : 32;
@@ -205,22 +226,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // fp32 MN-major operands must use the 32B-atom flavour of the 128B swizzle (4-row atoms)
       constexpr uint32_t A_LT = (TF32X3 && A_MN) ? 1u : 2u, B_LT = (TF32X3 && B_MN) ? 1u : 2u;
       constexpr uint32_t A_SBO = (TF32X3 && A_MN) ? 512u : 1024u, B_SBO = (TF32X3 && B_MN) ? 512u : 1024u;
+      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
+        if (CG == 2) tc_mma_2sm<TF32X3>(d, a, b, idesc, acc); else tc_mma<TF32X3>(d, a, b, idesc, acc);
+      };
+      auto commit = [&](uint32_t bar) { if (CG == 2) tc_commit_2sm(bar); else tc_commit(bar); };
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;  // accumulator hand-offs so far (one per K chunk)
-      for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int64_t tile = group; tile < p.total_tiles; tile += num_groups) {
         const TileCoord tc = decode_tile(p, tile);
         const int kb0 = tc.slice * p.kb_per_slice;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_slice);
         for (int kc0 = kb0; kc0 < kb1; kc0 += p.kb_per_chunk, ++it) {
           const int kc1 = min(kb1, kc0 + p.kb_per_chunk);
-          const int as = it & 1;
-          const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-          mbar_wait(tempty_bar(as), aphase ^ 1u);
+          const int as = it % ACC_STAGES;
+          const uint32_t aphase = (uint32_t)(it / ACC_STAGES) & 1u;
+          if (CG == 2) mbar_wait_cluster(tempty_bar(as), aphase ^ 1u); else mbar_wait(tempty_bar(as), aphase ^ 1u);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
           for (int kb = kc0; kb < kc1; ++kb) {
-            mbar_wait(TF32X3 ? split_bar(stage) : full_bar(stage), phase);
+            const uint32_t ready = TF32X3 ? split_bar(stage) : full_bar(stage);
+            if (CG == 2) mbar_wait_cluster(ready, phase); else mbar_wait(ready, phase);
             tc_fence_after();
             const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
             const uint32_t sB = sA + Cfg::A_BYTES;
@@ -232,44 +258,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (TF32X3) {
                 const uint64_t adesc_lo = make_smem_desc(sA + Cfg::RAW_BYTES + k * A_KSTEP, A_LBO, A_SBO, A_LT);
                 const uint64_t bdesc_lo = make_smem_desc(sB + Cfg::RAW_BYTES + k * B_KSTEP, B_LBO, B_SBO, B_LT);
-                tc_mma<true>(d_tmem, adesc_lo, bdesc, idesc, acc);
-                tc_mma<true>(d_tmem, adesc, bdesc_lo, idesc, 1u);
-                tc_mma<true>(d_tmem, adesc, bdesc, idesc, 1u);
+                mma(d_tmem, adesc_lo, bdesc, acc);
+                mma(d_tmem, adesc, bdesc_lo, 1u);
+                mma(d_tmem, adesc, bdesc, 1u);
               } else {
-                tc_mma<false>(d_tmem, adesc, bdesc, idesc, acc);
+                mma(d_tmem, adesc, bdesc, acc);
               }
             }
-            tc_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
+            commit(empty_bar(stage));  // smem slot (both CTAs) reusable once these MMAs retire
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
-          tc_commit(tfull_bar(as));  // chunk accumulator complete
+          commit(tfull_bar(as));  // chunk accumulator complete (both CTAs' epilogues)
         }
       }
     }
     __syncwarp();
-  } else if (warp >= 4 && warp < 8) {
-    // ===================== epilogue =====================
-    const int ew = warp & 3;  // TMEM lane quarter this warp may read
+  } else if (warp >= 4 && warp < 4 + Cfg::EPI_WARPS) {
+    // ===================== epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves =====================
+    const int ew = warp & 3;           // TMEM lane quarter this warp may read
+    const int ch = (warp - 4) >> 2;    // column half
+    constexpr int COLS_PER_WARP = BN / 2;
     const bool beta0 = (p.beta == 0.0f);
+    const uint32_t tempty_leader0 = (CG == 2) ? map_to_cta(tempty_bar(0), 0) : tempty_bar(0);
     int it = 0;
-    for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int64_t tile = group; tile < p.total_tiles; tile += num_groups) {
       const TileCoord tc = decode_tile(p, tile);
       const int kb0 = tc.slice * p.kb_per_slice;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_slice);
-      const int64_t m = (int64_t)tc.mt * BM + ew * 32 + lane;
-      const int64_t n0 = (int64_t)tc.nt * BN;
+      const int64_t m = (int64_t)tc.mt * Cfg::TILE_M + rank * BM + ew * 32 + lane;
+      const int64_t n0 = (int64_t)tc.nt * BN + ch * COLS_PER_WARP;
       const bool m_ok = m < p.M;
       for (int kc0 = kb0; kc0 < kb1; kc0 += p.kb_per_chunk, ++it) {
         const bool first = (kc0 == kb0), last = (kc0 + p.kb_per_chunk >= kb1);
-        const int as = it & 1;
-        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        const int as = it % ACC_STAGES;
+        const uint32_t aphase = (uint32_t)(it / ACC_STAGES) & 1u;
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
-        const uint32_t t_lane = tmem_base + ((uint32_t)(ew * 32) << 16);
+        const uint32_t t_lane = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ch * COLS_PER_WARP);
         const uint32_t t_row = t_lane + (uint32_t)(as * BN);
         const uint32_t t_sum = t_lane + (uint32_t)Cfg::RSUM_COL;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 32) {
           if (n0 + c0 >= p.N) break;  // warp-uniform
           uint32_t v[32];
           tmem_ld_32x32(t_row + c0, v);
@@ -310,16 +339,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (TF32X3 && !last) tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(as));
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(tempty_leader0 + 8u * as); else mbar_arrive(tempty_bar(as));
+        }
       }
     }
-  } else if (TF32X3 && warp >= 8) {
-    // ===================== fp32 -> (hi, lo) tf32 splitters =====================
-    const int st = threadIdx.x - 256;  // 0..127
+  } else if (TF32X3 && warp >= 4 + Cfg::EPI_WARPS) {
+    // ===================== fp32 -> (hi, lo) tf32 splitters (each CTA splits what it staged) ==============
+    const int st = threadIdx.x - 32 * (4 + Cfg::EPI_WARPS);
     int stage = 0;
     uint32_t phase = 0;
     constexpr int VEC_PER_STAGE = Cfg::RAW_BYTES / 16;
-    for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const uint32_t split_leader0 = (CG == 2) ? map_to_cta(split_bar(0), 0) : split_bar(0);
+    const bool raw_hi = p.raw_hi != 0;
+    for (int64_t tile = group; tile < p.total_tiles; tile += num_groups) {
       const TileCoord tc = decode_tile(p, tile);
       const int kb0 = tc.slice * p.kb_per_slice;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_slice);
@@ -329,36 +362,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float4* raw = reinterpret_cast<float4*>(smem_raw + (smem_base - smem_u32(smem_raw)) +
                                                 stage * Cfg::STAGE_BYTES);
         float4* lo = raw + VEC_PER_STAGE;
-#pragma unroll 4
-        for (int i = st; i < VEC_PER_STAGE; i += Cfg::NUM_SPLIT_THREADS) {
-          const float4 a = raw[i];
-          float4 h, l;
+        if (raw_hi) {
+          // hi operand = the raw fp32 tile (the tensor core reads only the tf32 bits, i.e. truncates);
+          // lo = rn_tf32(a - trunc_tf32(a)).  Halves the shared-memory writes of the splitter.
+          auto lo_of = [](float x) {
+            const float d = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+            uint32_t lb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(d == d ? d : 0.0f));  // inf - inf -> 0
+            return __uint_as_float(lb);
+          };
+#pragma unroll 8
+          for (int i = st; i < VEC_PER_STAGE; i += Cfg::NUM_SPLIT_THREADS) {
+            const float4 a = raw[i];
+            lo[i] = make_float4(lo_of(a.x), lo_of(a.y), lo_of(a.z), lo_of(a.w));
+          }
+        } else {
           auto split = [](float x, float& hi, float& lo_) {
             uint32_t hb;
             asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
             hi = __uint_as_float(hb);
-            const float d = (fabsf(hi) == INFINITY) ? 0.0f : x - hi;
+            const float d = x - hi;
             uint32_t lb;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(d));
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(d == d ? d : 0.0f));
             lo_ = __uint_as_float(lb);
           };
-          split(a.x, h.x, l.x);
-          split(a.y, h.y, l.y);
-          split(a.z, h.z, l.z);
-          split(a.w, h.w, l.w);
-          raw[i] = h;
-          lo[i] = l;
+#pragma unroll 4
+          for (int i = st; i < VEC_PER_STAGE; i += Cfg::NUM_SPLIT_THREADS) {
+            const float4 a = raw[i];
+            float4 h, l;
+            split(a.x, h.x, l.x);
+            split(a.y, h.y, l.y);
+            split(a.z, h.z, l.z);
+            split(a.w, h.w, l.w);
+            raw[i] = h;
+            lo[i] = l;
+          }
         }
         fence_proxy_async();
-        mbar_arrive(split_bar(stage));
+        if (CG == 2) mbar_arrive_cluster(split_leader0 + 8u * stage); else mbar_arrive(split_bar(stage));
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) {
+    if (CG == 2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
 }
 
 // ---- host side ---------------------------------------------------------------------------
@@ -395,27 +446,106 @@ bool make_operand_map(CUtensorMap* out, int es, CUtensorMapDataType dt, const vo
   return r == CUDA_SUCCESS;
 }
 
-template <typename TIn, typename TOut, int BN, int STAGES, bool A_MN, bool B_MN>
+template <typename TIn, typename TOut, int BN, int STAGES, bool A_MN, bool B_MN, int CG>
 int launch_inst(pbx_handle_t h, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p) {
-  using Cfg = TcCfg<sizeof(TIn), BN, STAGES>;
-  auto kern = gemm_tc_kernel<TIn, TOut, BN, STAGES, A_MN, B_MN>;
+  using Cfg = TcCfg<sizeof(TIn), BN, STAGES, CG>;
+  static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared memory budget");
+  auto kern = gemm_tc_kernel<TIn, TOut, BN, STAGES, A_MN, B_MN, CG>;
   PBX_CUDA_CHECK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  const int64_t grid = p.total_tiles < h->sm_count ? p.total_tiles : h->sm_count;
-  kern<<<(unsigned)grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, h->stream>>>(tmA, tmB, p);
+  const int64_t units = h->sm_count / CG;   // persistent: one CTA (or CTA pair) per SM (pair)
+  const int64_t groups = p.total_tiles < units ? p.total_tiles : units;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(groups * CG));
+  cfg.blockDim = dim3(Cfg::NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PBX_CUDA_CHECK(h, cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
   h->launches++;
-  PBX_CUDA_CHECK(h, cudaGetLastError());
   return PBX_OK;
 }
 
-template <typename TIn, typename TOut, int BN, int STAGES>
+template <typename TIn, typename TOut, int BN, int STAGES, int CG>
 int launch_major(pbx_handle_t h, bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB,
                  const TcParams& p) {
   if (a_mn) {
-    return b_mn ? launch_inst<TIn, TOut, BN, STAGES, true, true>(h, tmA, tmB, p)
-                : launch_inst<TIn, TOut, BN, STAGES, true, false>(h, tmA, tmB, p);
+    return b_mn ? launch_inst<TIn, TOut, BN, STAGES, true, true, CG>(h, tmA, tmB, p)
+                : launch_inst<TIn, TOut, BN, STAGES, true, false, CG>(h, tmA, tmB, p);
   }
-  return b_mn ? launch_inst<TIn, TOut, BN, STAGES, false, true>(h, tmA, tmB, p)
-              : launch_inst<TIn, TOut, BN, STAGES, false, false>(h, tmA, tmB, p);
+  return b_mn ? launch_inst<TIn, TOut, BN, STAGES, false, true, CG>(h, tmA, tmB, p)
+              : launch_inst<TIn, TOut, BN, STAGES, false, false, CG>(h, tmA, tmB, p);
+}
+
+// tile configurations, most efficient first: CTA pair 256x256, CTA pair 256x128, single CTA 128x128
+template <typename TIn, typename TOut>
+int launch_cfg(pbx_handle_t h, int cg, int bn, bool a_mn, bool b_mn, const CUtensorMap& tmA,
+               const CUtensorMap& tmB, const TcParams& p) {
+  constexpr bool F32 = sizeof(TIn) == 4;
+  if (cg == 2 && bn == 256) return launch_major<TIn, TOut, 256, F32 ? 3 : 6, 2>(h, a_mn, b_mn, tmA, tmB, p);
+  if (cg == 2) return launch_major<TIn, TOut, 128, F32 ? 4 : 8, 2>(h, a_mn, b_mn, tmA, tmB, p);
+  return launch_major<TIn, TOut, 128, F32 ? 3 : 6, 1>(h, a_mn, b_mn, tmA, tmB, p);
+}
+
+struct TcPlan {
+  int cg, bn, slices;
+};
+
+// Shape -> {cta_group, tile width, K slices}.  Replaces the reference's NVIDIA heuristics
+// (src/interface/blas3/backend/nvidia_gpu.hpp:116-171: tile by M,N thresholds) with the quantity
+// that matters on a 148-SM persistent kernel: how many tiles there are per SM (pair).
+TcPlan make_plan(pbx_handle_t h, const PbxGemmCall& c) {
+  const int64_t k_block = ROW_BYTES / (int64_t)pbx_in_size(c.dtype);
+  const int64_t kb = (c.k + k_block - 1) / k_block;
+  struct Cand { int cg, bn; };
+  const Cand cands[3] = {{2, 256}, {2, 128}, {1, 128}};
+  auto tiles_of = [&](const Cand& cd) {
+    return ((c.m + 128 * cd.cg - 1) / (128 * cd.cg)) * ((c.n + cd.bn - 1) / cd.bn) * c.batch;
+  };
+  auto usable = [&](const Cand& cd) { return !(cd.cg == 2 && c.m <= 128) && !(cd.bn == 256 && c.n <= 128); };
+  TcPlan plan = {1, 128, 1};
+  const char* force = getenv("PBX_TC_CONFIG");  // "cg,bn" (testing)
+  int fcg = 0, fbn = 0;
+  if (force && sscanf(force, "%d,%d", &fcg, &fbn) == 2 && (fcg == 1 || fcg == 2) && (fbn == 128 || (fbn == 256 && fcg == 2))) {
+    plan.cg = fcg; plan.bn = fbn;
+  } else {
+    bool found = false;
+    for (const Cand& cd : cands) {
+      if (!usable(cd)) continue;
+      const int64_t units = h->sm_count / cd.cg;
+      if (tiles_of(cd) * 10 >= units * 6) { plan.cg = cd.cg; plan.bn = cd.bn; found = true; break; }
+    }
+    if (!found) {
+      // too few tiles for any config: take the biggest usable tile if K is deep enough to be split
+      // across the machine, else the smallest tile (most CTAs)
+      const bool deep = c.k >= 2 * 2048;
+      for (const Cand& cd : cands) {
+        if (!usable(cd)) continue;
+        plan.cg = cd.cg; plan.bn = cd.bn;
+        if (deep) break;
+      }
+    }
+  }
+  // K slices: the reference splits by depth = ceil(4*CUs / tiles) when K > 2048
+  // (gemm_partial_local.hpp:191-199, portblas_handle.hpp:323); here: up to two waves of the machine.
+  const Cand chosen = {plan.cg, plan.bn};
+  const int64_t tiles = tiles_of(chosen), units = h->sm_count / plan.cg;
+  int64_t slices = 1;
+  if (h->forced_split_k > 1) slices = h->forced_split_k;
+  else if (h->forced_split_k == 0 && tiles * 2 <= units && c.k >= 2 * 2048) {
+    slices = (2 * units) / tiles;
+    if (slices > c.k / 2048) slices = c.k / 2048;
+  }
+  if (slices > kb) slices = kb;
+  if (slices < 1) slices = 1;
+  const int64_t kbps = (kb + slices - 1) / slices;
+  plan.slices = (int)((kb + kbps - 1) / kbps);  // drop empty trailing slices
+  return plan;
 }
 
 }  // namespace
@@ -434,23 +564,22 @@ bool pbx_tcgen05_eligible(pbx_handle_t h, const PbxGemmCall& c) {
   return get_encode_fn() != nullptr;
 }
 
+int pbx_tcgen05_slices(pbx_handle_t h, const PbxGemmCall& c) { return make_plan(h, c).slices; }
+
 int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
   const int es = (int)pbx_in_size(c.dtype);
   const bool f32 = (c.dtype == PBX_F32);
   const int bk = ROW_BYTES / es;
-  // tile width: 256 columns when the problem is wide enough to keep 148 SMs busy with it
-  int bn = 128;
-  if (!f32) {
-    const int64_t tiles256 = ((c.m + BM - 1) / BM) * ((c.n + 255) / 256) * c.batch * slices;
-    if (c.n > 128 && tiles256 >= h->sm_count) bn = 256;
-  }
+  TcPlan plan = make_plan(h, c);
+  plan.slices = slices;
+  const int bn = plan.bn, cg = plan.cg;
   const bool a_mn = !c.ta, b_mn = c.tb;
   CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                : ((c.dtype == PBX_F16 || c.dtype == PBX_F16_F32) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
                                                                                 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
   CUtensorMap tmA, tmB;
   if (!make_operand_map(&tmA, es, dt, c.A, c.m, c.k, c.lda, c.batch, c.sa, !a_mn, BM) ||
-      !make_operand_map(&tmB, es, dt, c.B, c.n, c.k, c.ldb, c.batch, c.sb, !b_mn, bn)) {
+      !make_operand_map(&tmB, es, dt, c.B, c.n, c.k, c.ldb, c.batch, c.sb, !b_mn, bn / cg)) {
     h->last_error = "cuTensorMapEncodeTiled failed";
     return PBX_ERR_CUDA;
   }
@@ -459,32 +588,28 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
   p.M = c.m; p.N = c.n; p.K = c.k; p.ldc = c.ldc; p.sc = c.sc;
   p.alpha = (float)c.alpha; p.beta = (float)c.beta;
   p.batch = (int)c.batch; p.slices = slices;
-  p.m_tiles = (int)((c.m + BM - 1) / BM);
+  p.m_tiles = (int)((c.m + BM * cg - 1) / (BM * cg));
   p.n_tiles = (int)((c.n + bn - 1) / bn);
-  p.group_m = 8;
+  p.group_m = cg == 2 ? 8 : 16;
   p.kb_total = (int)((c.k + bk - 1) / bk);
   p.kb_per_slice = (p.kb_total + slices - 1) / slices;
-  // fp32: 16 blocks x 32 = 512 k per tensor-core accumulation chain (~4e-6 relative bias per chunk)
-  p.kb_per_chunk = f32 ? 16 : (1 << 30);
+  // fp32: the tensor core truncates when it adds into its fp32 accumulator, so an accumulation
+  // chain is limited to kb_per_chunk blocks of 32 (default 16 -> 512 k: ~4e-6 relative bias)
+  const int chunk_env = getenv("PBX_TF32_CHUNK_KB") ? atoi(getenv("PBX_TF32_CHUNK_KB")) : 0;
+  p.kb_per_chunk = f32 ? (chunk_env > 0 ? chunk_env : 16) : (1 << 30);
+  // default: raw fp32 tile as the hi operand (verified on B200: kind::tf32 ignores the low 13 mantissa bits)
+  const int raw_hi_env = getenv("PBX_TF32_RAW_HI") ? atoi(getenv("PBX_TF32_RAW_HI")) : 1;
+  p.raw_hi = raw_hi_env;
   p.a_batched = (c.batch > 1 && c.sa > 0) ? 1 : 0;
   p.b_batched = (c.batch > 1 && c.sb > 0) ? 1 : 0;
   p.total_tiles = (int64_t)p.m_tiles * p.n_tiles * c.batch * slices;
 
   switch (c.dtype) {
-    case PBX_F32:
-      return launch_major<float, float, 128, 3>(h, a_mn, b_mn, tmA, tmB, p);
-    case PBX_F16:
-      return bn == 256 ? launch_major<__half, __half, 256, 4>(h, a_mn, b_mn, tmA, tmB, p)
-                       : launch_major<__half, __half, 128, 6>(h, a_mn, b_mn, tmA, tmB, p);
-    case PBX_F16_F32:
-      return bn == 256 ? launch_major<__half, float, 256, 4>(h, a_mn, b_mn, tmA, tmB, p)
-                       : launch_major<__half, float, 128, 6>(h, a_mn, b_mn, tmA, tmB, p);
-    case PBX_BF16:
-      return bn == 256 ? launch_major<__nv_bfloat16, __nv_bfloat16, 256, 4>(h, a_mn, b_mn, tmA, tmB, p)
-                       : launch_major<__nv_bfloat16, __nv_bfloat16, 128, 6>(h, a_mn, b_mn, tmA, tmB, p);
-    case PBX_BF16_F32:
-      return bn == 256 ? launch_major<__nv_bfloat16, float, 256, 4>(h, a_mn, b_mn, tmA, tmB, p)
-                       : launch_major<__nv_bfloat16, float, 128, 6>(h, a_mn, b_mn, tmA, tmB, p);
+    case PBX_F32: return launch_cfg<float, float>(h, cg, bn, a_mn, b_mn, tmA, tmB, p);
+    case PBX_F16: return launch_cfg<__half, __half>(h, cg, bn, a_mn, b_mn, tmA, tmB, p);
+    case PBX_F16_F32: return launch_cfg<__half, float>(h, cg, bn, a_mn, b_mn, tmA, tmB, p);
+    case PBX_BF16: return launch_cfg<__nv_bfloat16, __nv_bfloat16>(h, cg, bn, a_mn, b_mn, tmA, tmB, p);
+    case PBX_BF16_F32: return launch_cfg<__nv_bfloat16, float>(h, cg, bn, a_mn, b_mn, tmA, tmB, p);
   }
   return PBX_ERR_INVALID_ARG;
 }

@@ -163,7 +163,7 @@ static int run_gemm(pbx_handle_t h, const PbxGemmCall& c, int batch_type) {
 
   int slices = 1;
   const size_t acc_size = (c.dtype == PBX_F64) ? 8 : 4;
-  if (kernel == PBX_KERNEL_TCGEN05) slices = choose_split_k(h, c, 128, 128, c.dtype == PBX_F32 ? 32 : 64, 2048);
+  if (kernel == PBX_KERNEL_TCGEN05) slices = pbx_tcgen05_slices(h, c);
   else if (kernel == PBX_KERNEL_DMMA) slices = choose_split_k(h, c, 128, 128, 16, 1024);
   else slices = choose_split_k(h, c, 64, 64, 16, 1024);
   if (slices > 1) {

@@ -84,5 +84,6 @@ int pbx_launch_scal(pbx_handle_t h, int dtype, int64_t m, int64_t n, double beta
                     int64_t ldc, int64_t stridec, int64_t batch, int interleaved);
 int pbx_launch_splitk_reduce(pbx_handle_t h, const PbxGemmCall& c, int slices);
 bool pbx_tcgen05_eligible(pbx_handle_t h, const PbxGemmCall& c);
+int pbx_tcgen05_slices(pbx_handle_t h, const PbxGemmCall& c);  // K slices the tcgen05 plan wants
 int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices);
 int pbx_launch_dmma(pbx_handle_t h, const PbxGemmCall& c, int slices);

@@ -53,12 +53,13 @@ class Case:
     seed: int = 12345
     kernel: int = 0                # forced pbx_kernel_t (0 = auto)
     split_k: int = 0
+    env: tuple = ()                # ((name, value), ...) set around the call (PBX_TC_CONFIG, PBX_TF32_RAW_HI ...)
 
     def ident(self) -> str:
         return (f"{self.dtype}-{self.api}-{self.transa}{self.transb}-{self.m}x{self.n}x{self.k}-a{self.alpha}"
                 f"b{self.beta}-ld{self.lda_mul}{self.ldb_mul}{self.ldc_mul}-off{self.offset}-bs{self.batch}"
                 f"t{self.batch_type}-s{self.stride_a_mul}{self.stride_b_mul}{self.stride_c_mul}"
-                f"-k{self.kernel}-sk{self.split_k}")
+                f"-k{self.kernel}-sk{self.split_k}" + "".join(f"-{name[4:]}={val}" for name, val in self.env))
 
 
 @dataclasses.dataclass
@@ -147,6 +148,10 @@ def run_case(handle: blas.SB_Handle, cs: Case) -> Result:
 
     handle.set_forced_kernel(cs.kernel)
     handle.set_split_k(cs.split_k)
+    import os
+    saved_env = {name: os.environ.get(name) for name, _ in cs.env}
+    for name, val in cs.env:
+        os.environ[name] = str(val)
     status_text = ""
     try:
         if cs.api == "gemm":
@@ -164,6 +169,11 @@ def run_case(handle: blas.SB_Handle, cs: Case) -> Result:
     finally:
         handle.set_forced_kernel(0)
         handle.set_split_k(0)
+        for name, old in saved_env.items():
+            if old is None:
+                os.environ.pop(name, None)
+            else:
+                os.environ[name] = old
     kern, sk = handle.last_kernel, handle.last_split_k
     if st_exp != 0 or status_text:
         ok = oracle.STATUS_TEXT.get(st_exp, "?") == status_text

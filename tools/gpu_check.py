@@ -117,6 +117,25 @@ if __name__ == "__main__":
                                                  for (ta, tb), (m, n, k), b in itertools.product(
                                                      TRANS, [(128, 128, 32), (128, 128, 256), (136, 264, 520),
                                                              (2200, 264, 40), (1024, 1536, 1536)], [0.0, 0.5])])
+    if want("tccfg"):
+        # every tcgen05 tile configuration (cta_group, BN) on ragged and aligned shapes
+        for cfgs in ["1,128", "2,128", "2,256"]:
+            for dt in ["bf16f32", "f16", "f32"]:
+                envs = [(("PBX_TC_CONFIG", cfgs),)]
+                if dt == "f32":
+                    envs.append((("PBX_TC_CONFIG", cfgs), ("PBX_TF32_RAW_HI", 1)))
+                for env in envs:
+                    bad += sweep(h, f"tcgen05 cfg={cfgs} {dt} {env[1:] if len(env) > 1 else ''}",
+                                 [Case(dtype=dt, transa=ta, transb=tb, m=m, n=n, k=k, beta=b, kernel=2, env=env)
+                                  for (ta, tb), (m, n, k), b in itertools.product(
+                                      TRANS, [(256, 256, 64), (136, 264, 520), (2200, 264, 40), (1024, 1536, 1536),
+                                              (520, 136, 4104)], [0.0, 0.5])])
+            bad += sweep(h, f"tcgen05 cfg={cfgs} batched/split", [
+                Case(dtype=dt, api="strided", transa=ta, transb=tb, m=256, n=256, k=256, alpha=1.0, beta=0.0, batch=6,
+                     stride_a_mul=sa, stride_b_mul=1, kernel=2, env=(("PBX_TC_CONFIG", cfgs),))
+                for dt, (ta, tb), sa in itertools.product(["bf16", "f32"], TRANS, [0, 1])] + [
+                Case(dtype=dt, transa=ta, transb=tb, m=264, n=136, k=16416, beta=0.5, kernel=2, split_k=3,
+                     env=(("PBX_TC_CONFIG", cfgs),)) for dt, (ta, tb) in itertools.product(["bf16f32", "f32"], TRANS)])
     if want("batched"):
         for dt in ["f32", "f64", "bf16", "f16f32"]:
             bad += sweep(h, f"batched {dt}", [Case(dtype=dt, api="batched", transa=ta, transb=tb, m=m, n=n, k=k,
