@@ -10,6 +10,8 @@
 // doubles so every 64-bit fragment load is bank-conflict free per half-warp.
 #include <stdio.h>
 
+#include <type_traits>
+
 #include "pbx_internal.cuh"
 
 namespace {
@@ -48,36 +50,65 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// Load one 128 x 16 operand tile.  X(mn,k) lives at  KContig ? X[k + mn*ld] : X[mn + k*ld].
-// KContig tiles go to smem as [mn][k] (stride LD_K), the others as [k][mn] (stride LD_MN).
+// Per-thread copy plan of one operand: chunk i of this thread covers VEC doubles at
+//   KContig : (mn = mn_t + i*MN_STEP, k = k_t)        MN_STEP = 256 / (DBK/VEC)
+//   else    : (mn = mn_t,             k = k_t + i*K_STEP)   K_STEP = 256 / (DBM/VEC)
+// The global pointer of chunk 0 advances by a constant per K block, so the interior fast path
+// is one 64-bit add per operand per K block plus PER_THREAD cp.async with immediate offsets.
 template <bool KContig, int VEC>
-__device__ __forceinline__ void load_tile(double* smem_tile, const double* __restrict__ X, int64_t ld,
-                                          int64_t mn0, int64_t k0, int64_t mn_total, int64_t k_end, int tid) {
-  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_tile);
-  constexpr int CHUNKS = DBM * DBK / VEC;          // 1024 (VEC=2) or 2048
-  constexpr int PER_THREAD = CHUNKS / 256;
-#pragma unroll
-  for (int i = 0; i < PER_THREAD; ++i) {
-    const int c = tid + i * 256;
-    int mn, kk;
-    if (KContig) { kk = (c % (DBK / VEC)) * VEC; mn = c / (DBK / VEC); }
-    else         { mn = (c % (DBM / VEC)) * VEC; kk = c / (DBM / VEC); }
-    const int64_t gmn = mn0 + mn, gk = k0 + kk;
-    int valid;  // elements of this chunk that exist
-    if (KContig) valid = (gmn < mn_total) ? (int)min((int64_t)VEC, max((int64_t)0, k_end - gk)) : 0;
-    else         valid = (gk < k_end) ? (int)min((int64_t)VEC, max((int64_t)0, mn_total - gmn)) : 0;
-    const double* src = valid > 0 ? (KContig ? X + gk + gmn * ld : X + gmn + gk * ld) : X;
-    const uint32_t dst = sbase + (uint32_t)((KContig ? mn * LD_K + kk : kk * LD_MN + mn) * 8);
-    if (VEC == 2) cp_async_16(dst, src, valid * 8);
-    else cp_async_8(dst, src, valid * 8);
+struct TilePlan {
+  static constexpr int CHUNKS = DBM * DBK / VEC;
+  static constexpr int PER_THREAD = CHUNKS / 256;
+  static constexpr int MN_STEP = KContig ? 256 / (DBK / VEC) : 0;
+  static constexpr int K_STEP = KContig ? 0 : 256 / (DBM / VEC);
+  static constexpr int DST_STEP = (KContig ? MN_STEP * LD_K : K_STEP * LD_MN) * 8;  // bytes between chunks
+  const double* src;     // chunk 0 at the current K block
+  int64_t chunk_stride;  // elements between consecutive chunks of this thread
+  int64_t kb_stride;     // elements per K block
+  uint32_t dst0;         // byte offset of chunk 0 inside a stage tile
+  int mn_t, k_t;
+  __device__ __forceinline__ void init(const double* X, int64_t ld, int64_t mn0, int64_t k0, int tid) {
+    if (KContig) { k_t = (tid % (DBK / VEC)) * VEC; mn_t = tid / (DBK / VEC); }
+    else         { mn_t = (tid % (DBM / VEC)) * VEC; k_t = tid / (DBM / VEC); }
+    src = KContig ? X + (k0 + k_t) + (mn0 + mn_t) * ld : X + (mn0 + mn_t) + (k0 + k_t) * ld;
+    chunk_stride = KContig ? (int64_t)MN_STEP * ld : (int64_t)K_STEP * ld;
+    kb_stride = KContig ? (int64_t)DBK : (int64_t)DBK * ld;
+    dst0 = (uint32_t)((KContig ? mn_t * LD_K + k_t : k_t * LD_MN + mn_t) * 8);
   }
-}
+  // chunks [I0, I1) of the tile, all elements known to exist
+  template <int I0, int I1>
+  __device__ __forceinline__ void copy_full(uint32_t stage_base) const {
+#pragma unroll
+    for (int i = I0; i < I1; ++i) {
+      if (VEC == 2) cp_async_16(stage_base + dst0 + i * DST_STEP, src + i * chunk_stride, 16);
+      else cp_async_8(stage_base + dst0 + i * DST_STEP, src + i * chunk_stride, 8);
+    }
+  }
+  // same with per-chunk edge predication (zero fill)
+  template <int I0, int I1>
+  __device__ __forceinline__ void copy_edge(uint32_t stage_base, const double* X, int64_t mn0, int64_t k0,
+                                            int64_t mn_total, int64_t k_end) const {
+#pragma unroll
+    for (int i = I0; i < I1; ++i) {
+      const int64_t gmn = mn0 + mn_t + (KContig ? i * MN_STEP : 0);
+      const int64_t gk = k0 + k_t + (KContig ? 0 : i * K_STEP);
+      int valid;
+      if (KContig) valid = (gmn < mn_total) ? (int)min((int64_t)VEC, max((int64_t)0, k_end - gk)) : 0;
+      else         valid = (gk < k_end) ? (int)min((int64_t)VEC, max((int64_t)0, mn_total - gmn)) : 0;
+      const double* sp = valid > 0 ? src + i * chunk_stride : X;
+      if (VEC == 2) cp_async_16(stage_base + dst0 + i * DST_STEP, sp, valid * 8);
+      else cp_async_8(stage_base + dst0 + i * DST_STEP, sp, valid * 8);
+    }
+  }
+};
 
 template <bool AK, bool BK_, int VEC>
 __global__ void __launch_bounds__(256, 1) gemm_dmma_kernel(DmmaParams p) {
   extern __shared__ __align__(16) double dsmem[];
   double* sA = dsmem;
   double* sB = dsmem + DSTAGES * TILE_ELEMS;
+  const uint32_t sA_u32 = (uint32_t)__cvta_generic_to_shared(sA);
+  const uint32_t sB_u32 = (uint32_t)__cvta_generic_to_shared(sB);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm0 = (warp & 1) * 64, wn0 = (warp >> 1) * 32;
   const int lr = lane >> 2, lc = lane & 3;
@@ -96,6 +127,10 @@ __global__ void __launch_bounds__(256, 1) gemm_dmma_kernel(DmmaParams p) {
   const int64_t kb_beg = (int64_t)slice * p.kb_per_slice;
   const int64_t kb_end = min(kb_total, kb_beg + p.kb_per_slice);
   const int nkb = (int)(kb_end - kb_beg);
+  // interior tile: every row/column of the 128x128 tile exists -> only the last K block may need predication
+  const bool a_full = (m0 + DBM <= p.m), b_full = (n0 + DBN <= p.n);
+  constexpr int PT = TilePlan<AK, VEC>::PER_THREAD;   // cp.async per thread per operand per K block (4 or 8)
+  constexpr int Q = PT / 4;                            // issued per k4 step
 
   for (int64_t b = blockIdx.z; b < p.batch; b += gridDim.z) {
     const double* A = p.A + b * p.sa;
@@ -106,22 +141,44 @@ __global__ void __launch_bounds__(256, 1) gemm_dmma_kernel(DmmaParams p) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    auto issue = [&](int kb_local) {
-      if (kb_local < nkb) {
-        const int s = kb_local % DSTAGES;
-        const int64_t k0 = (kb_beg + kb_local) * DBK;
-        load_tile<AK, VEC>(sA + s * TILE_ELEMS, A, p.lda, m0, k0, p.m, p.k, tid);
-        load_tile<BK_, VEC>(sB + s * TILE_ELEMS, B, p.ldb, n0, k0, p.n, p.k, tid);
+    TilePlan<AK, VEC> pa;
+    TilePlan<BK_, VEC> pb;
+    pa.init(A, p.lda, m0, kb_beg * DBK, tid);
+    pb.init(B, p.ldb, n0, kb_beg * DBK, tid);
+    int issued = 0;  // K blocks whose copies have been issued (plans point at block `issued`)
+
+    // quarter q (0..3) of the copies of K block `issued` into its ring slot
+    auto issue_part = [&](auto qc) {
+      constexpr int q = decltype(qc)::value;
+      if (issued < nkb) {
+        const int s = issued % DSTAGES;
+        const int64_t k0 = (kb_beg + issued) * DBK;
+        const uint32_t da = sA_u32 + (uint32_t)(s * TILE_ELEMS * 8), db = sB_u32 + (uint32_t)(s * TILE_ELEMS * 8);
+        const bool k_full = (k0 + DBK <= p.k);
+        if (a_full && k_full) pa.template copy_full<q * Q, (q + 1) * Q>(da);
+        else pa.template copy_edge<q * Q, (q + 1) * Q>(da, A, m0, k0, p.m, p.k);
+        if (b_full && k_full) pb.template copy_full<q * Q, (q + 1) * Q>(db);
+        else pb.template copy_edge<q * Q, (q + 1) * Q>(db, B, n0, k0, p.n, p.k);
       }
+    };
+    auto issue_done = [&]() {
+      if (issued < nkb) { pa.src += pa.kb_stride; pb.src += pb.kb_stride; }
+      ++issued;
       cp_async_commit();
     };
+    using Q0 = std::integral_constant<int, 0>; using Q1 = std::integral_constant<int, 1>;
+    using Q2 = std::integral_constant<int, 2>; using Q3 = std::integral_constant<int, 3>;
 #pragma unroll
-    for (int s = 0; s < DSTAGES - 1; ++s) issue(s);
+    for (int s = 0; s < DSTAGES - 1; ++s) {
+      issue_part(Q0{}); issue_part(Q1{}); issue_part(Q2{}); issue_part(Q3{});
+      issue_done();
+    }
 
     for (int kb = 0; kb < nkb; ++kb) {
       cp_async_wait<DSTAGES - 2>();
       __syncthreads();
-      issue(kb + DSTAGES - 1);  // refills the stage consumed in iteration kb-1
+      // the copies of block kb+DSTAGES-1 (into the slot consumed in iteration kb-1) are spread over the
+      // four k4 steps so that the tensor pipe never waits behind a burst of address arithmetic
       const double* tA = sA + (kb % DSTAGES) * TILE_ELEMS;
       const double* tB = sB + (kb % DSTAGES) * TILE_ELEMS;
 #pragma unroll
@@ -137,11 +194,16 @@ __global__ void __launch_bounds__(256, 1) gemm_dmma_kernel(DmmaParams p) {
           const int c = wn0 + j * 8 + lr;
           bf[j] = BK_ ? tB[c * LD_K + kk + lc] : tB[(kk + lc) * LD_MN + c];
         }
+        if (kk == 0) issue_part(Q0{});
+        else if (kk == 4) issue_part(Q1{});
+        else if (kk == 8) issue_part(Q2{});
+        else issue_part(Q3{});
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
       }
+      issue_done();
     }
     cp_async_wait<0>();
     __syncthreads();

@@ -51,6 +51,7 @@ struct TcParams {
   int kb_per_chunk;  // K blocks accumulated inside the tensor core before an fp32 RN add (see below)
   int raw_hi;        // fp32: 1 = feed raw fp32 as the hi operand (hardware truncates to tf32)
   int a_batched, b_batched;
+  int tma_store;     // 16-bit C through shared memory + TMA store (needs beta == 0, aligned C, no split-K)
   int64_t total_tiles;
 };
 
@@ -74,7 +75,7 @@ constexpr int ROW_BYTES = 128;  // one swizzle row
 // CG = 1: one CTA computes a 128 x BN tile.  CG = 2: a CTA pair (2-CTA cluster, cta_group::2)
 // computes a 256 x BN tile; each CTA stages its own 128 rows of A and BN/2 rows of B, so the
 // shared-memory read rate per SM halves for the same MMA rate.
-template <int ES, int BN, int STAGES, int CG>
+template <int ES, int BN, int STAGES, int CG, int OS = 4>
 struct TcCfg {
   static constexpr bool TF32X3 = (ES == 4);
   static constexpr int BK = ROW_BYTES / ES;        // 64 (16-bit) or 32 (fp32) elements
@@ -86,12 +87,16 @@ struct TcCfg {
   static constexpr int RAW_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGE_BYTES = RAW_BYTES * (TF32X3 ? 2 : 1);  // + lo copies
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + align slack
+  static constexpr int EPI_WARPS = 8;
+  // 16-bit outputs: every epilogue warp owns two 32x32 staging tiles (column-major, rows contiguous)
+  // that it hands to TMA stores, so C leaves the SM as bulk writes instead of 2-byte stores
+  static constexpr int EPI_TILE_BYTES = 32 * 32 * OS;
+  static constexpr int EPI_BYTES = (OS == 2) ? EPI_WARPS * 2 * EPI_TILE_BYTES : 0;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // + align slack
   // TMEM: ACC_STAGES accumulators of BN columns (+ for fp32 a BN-column running sum)
   static constexpr int ACC_STAGES = TF32X3 ? ((3 * BN <= 512) ? 2 : 1) : 2;
   static constexpr int RSUM_COL = ACC_STAGES * BN;
   static constexpr int TMEM_COLS = TF32X3 ? 512 : 2 * BN;
-  static constexpr int EPI_WARPS = 8;
   static constexpr int SPLIT_WARPS = TF32X3 ? 4 : 0;
   static constexpr int NUM_THREADS = 32 * (4 + EPI_WARPS + SPLIT_WARPS);
   static constexpr int NUM_SPLIT_THREADS = 32 * SPLIT_WARPS;
@@ -119,10 +124,10 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int64_t tile
 }
 
 template <typename TIn, typename TOut, int BN, int STAGES, bool A_MN, bool B_MN, int CG>
-__global__ void __launch_bounds__(TcCfg<sizeof(TIn), BN, STAGES, CG>::NUM_THREADS, 1)
+__global__ void __launch_bounds__(TcCfg<sizeof(TIn), BN, STAGES, CG, sizeof(TOut)>::NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const TcParams p) {
-  using Cfg = TcCfg<sizeof(TIn), BN, STAGES, CG>;
+               const __grid_constant__ CUtensorMap tmC, const TcParams p) {
+  using Cfg = TcCfg<sizeof(TIn), BN, STAGES, CG, sizeof(TOut)>;
   constexpr bool TF32X3 = Cfg::TF32X3;
   constexpr int BK = Cfg::BK;
   constexpr int ACC_STAGES = Cfg::ACC_STAGES;
@@ -130,7 +135,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t epi_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = epi_base + Cfg::EPI_BYTES;
   // barrier map (8 B each): full[S] | empty[S] | split[S] | tmem_full[2] | tmem_empty[2] | tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -149,6 +155,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (Cfg::EPI_BYTES > 0 && p.tma_store) tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -241,12 +248,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int kc1 = min(kb1, kc0 + p.kb_per_chunk);
           const int as = it % ACC_STAGES;
           const uint32_t aphase = (uint32_t)(it / ACC_STAGES) & 1u;
-          if (CG == 2) mbar_wait_cluster(tempty_bar(as), aphase ^ 1u); else mbar_wait(tempty_bar(as), aphase ^ 1u);
+          mbar_wait(tempty_bar(as), aphase ^ 1u);   // only TMEM state is handed over (tcgen05 fences order it)
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
           for (int kb = kc0; kb < kc1; ++kb) {
             const uint32_t ready = TF32X3 ? split_bar(stage) : full_bar(stage);
-            if (CG == 2) mbar_wait_cluster(ready, phase); else mbar_wait(ready, phase);
+            // fp32 pair mode: the peer's splitter warps wrote shared memory with ordinary stores
+            if (CG == 2 && TF32X3) mbar_wait_cluster(ready, phase); else mbar_wait(ready, phase);
             tc_fence_after();
             const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
             const uint32_t sB = sA + Cfg::A_BYTES;
@@ -278,16 +286,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ew = warp & 3;           // TMEM lane quarter this warp may read
     const int ch = (warp - 4) >> 2;    // column half
     constexpr int COLS_PER_WARP = BN / 2;
+    constexpr bool OUT16 = (sizeof(TOut) == 2);
     const bool beta0 = (p.beta == 0.0f);
+    const bool tma_store = OUT16 && p.tma_store;
     const uint32_t tempty_leader0 = (CG == 2) ? map_to_cta(tempty_bar(0), 0) : tempty_bar(0);
+    // staging tiles of this warp (16-bit outputs): [buffer][column][32 rows]
+    const uint32_t stage_u32 = epi_base + (uint32_t)((warp - 4) * 2 * Cfg::EPI_TILE_BYTES);
+    TOut* stage_ptr = reinterpret_cast<TOut*>(smem_raw + (stage_u32 - smem_u32(smem_raw)));
+    uint32_t store_blk = 0;
     int it = 0;
     for (int64_t tile = group; tile < p.total_tiles; tile += num_groups) {
       const TileCoord tc = decode_tile(p, tile);
       const int kb0 = tc.slice * p.kb_per_slice;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_slice);
-      const int64_t m = (int64_t)tc.mt * Cfg::TILE_M + rank * BM + ew * 32 + lane;
+      const int64_t m_warp = (int64_t)tc.mt * Cfg::TILE_M + rank * BM + ew * 32;   // first row of this warp
+      const int64_t m = m_warp + lane;
       const int64_t n0 = (int64_t)tc.nt * BN + ch * COLS_PER_WARP;
       const bool m_ok = m < p.M;
+      const bool rows_full = (m_warp + 32 <= p.M);   // warp-uniform
       for (int kc0 = kb0; kc0 < kb1; kc0 += p.kb_per_chunk, ++it) {
         const bool first = (kc0 == kb0), last = (kc0 + p.kb_per_chunk >= kb1);
         const int as = it % ACC_STAGES;
@@ -299,7 +315,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t t_sum = t_lane + (uint32_t)Cfg::RSUM_COL;
 #pragma unroll 1
         for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 32) {
-          if (n0 + c0 >= p.N) break;  // warp-uniform
+          if (n0 + c0 >= p.N || m_warp >= p.M) break;  // warp-uniform
           uint32_t v[32];
           tmem_ld_32x32(t_row + c0, v);
           if (TF32X3 && !first) {
@@ -315,23 +331,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tmem_st_32x32(t_sum + c0, v);
             continue;
           }
+          const bool full = rows_full && (n0 + c0 + 32 <= p.N);   // warp-uniform: no predicate per element
           if (p.slices > 1) {
-            float* ws = p.ws + (((int64_t)tc.b * p.slices + tc.slice) * p.N) * p.M;
+            float* ws = p.ws + (((int64_t)tc.b * p.slices + tc.slice) * p.N + (n0 + c0)) * p.M + m;
+            if (full) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int64_t n = n0 + c0 + j;
-              if (m_ok && n < p.N) ws[n * p.M + m] = __uint_as_float(v[j]);
+              for (int j = 0; j < 32; ++j) ws[(int64_t)j * p.M] = __uint_as_float(v[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (m_ok && n0 + c0 + j < p.N) ws[(int64_t)j * p.M] = __uint_as_float(v[j]);
+            }
+          } else if (OUT16 && tma_store) {
+            // registers -> staging tile (a warp writes 64 contiguous bytes per column: conflict-free)
+            // -> one TMA store of the 32x32 box; rows / columns outside C are clipped by the hardware
+            const uint32_t buf = store_blk & 1u;
+            ++store_blk;
+            if (lane == 0) bulk_wait_read<1>();   // the store that last used this buffer has read it
+            __syncwarp();
+            TOut* st = stage_ptr + buf * (Cfg::EPI_TILE_BYTES / (int)sizeof(TOut)) + lane;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) OutCvt<TOut>::store(st + j * 32, p.alpha * __uint_as_float(v[j]));
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&tmC, stage_u32 + buf * Cfg::EPI_TILE_BYTES, (int)m_warp, (int)(n0 + c0), tc.b);
+              bulk_commit();
             }
           } else {
-            TOut* C = reinterpret_cast<TOut*>(p.C) + (int64_t)tc.b * p.sc;
+            TOut* dst = reinterpret_cast<TOut*>(p.C) + (int64_t)tc.b * p.sc + m + (n0 + c0) * p.ldc;
+            if (full) {
+              if (beta0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int64_t n = n0 + c0 + j;
-              if (m_ok && n < p.N) {
-                TOut* dst = C + m + n * p.ldc;
-                float r = p.alpha * __uint_as_float(v[j]);
-                if (!beta0) r += p.beta * OutCvt<TOut>::load(dst);
-                OutCvt<TOut>::store(dst, r);
+                for (int j = 0; j < 32; ++j) OutCvt<TOut>::store(dst + j * p.ldc, p.alpha * __uint_as_float(v[j]));
+              } else {
+#pragma unroll
+                for (int j0 = 0; j0 < 32; j0 += 8) {   // 8 loads in flight, then 8 stores
+                  float cin[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) cin[j] = OutCvt<TOut>::load(dst + (j0 + j) * p.ldc);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    OutCvt<TOut>::store(dst + (j0 + j) * p.ldc,
+                                        p.alpha * __uint_as_float(v[j0 + j]) + p.beta * cin[j]);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (m_ok && n0 + c0 + j < p.N) {
+                  float r = p.alpha * __uint_as_float(v[j]);
+                  if (!beta0) r += p.beta * OutCvt<TOut>::load(dst + j * p.ldc);
+                  OutCvt<TOut>::store(dst + j * p.ldc, r);
+                }
               }
             }
           }
@@ -340,10 +392,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (CG == 2) mbar_arrive_cluster(tempty_leader0 + 8u * as); else mbar_arrive(tempty_bar(as));
+          if (CG == 2) mbar_arrive_remote(tempty_leader0 + 8u * as); else mbar_arrive(tempty_bar(as));
         }
       }
     }
+    if (OUT16 && tma_store && lane == 0) bulk_wait_read<0>();   // staging tiles must outlive their stores
+    __syncwarp();
   } else if (TF32X3 && warp >= 4 + Cfg::EPI_WARPS) {
     // ===================== fp32 -> (hi, lo) tf32 splitters (each CTA splits what it staged) ==============
     const int st = threadIdx.x - 32 * (4 + Cfg::EPI_WARPS);
@@ -446,9 +500,25 @@ bool make_operand_map(CUtensorMap* out, int es, CUtensorMapDataType dt, const vo
   return r == CUDA_SUCCESS;
 }
 
+// Tensor map of C for the TMA-store epilogue: 32 x 32 boxes of the column-major output, no swizzle.
+bool make_c_map(CUtensorMap* out, int es, CUtensorMapDataType dt, void* ptr, int64_t m, int64_t n, int64_t ld,
+                int64_t batch, int64_t stride) {
+  auto fn = get_encode_fn();
+  if (!fn) return false;
+  const bool batched = batch > 1;
+  cuuint64_t dims[3] = {(cuuint64_t)m, (cuuint64_t)n, (cuuint64_t)(batched ? batch : 1)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * es, (cuuint64_t)(batched ? stride : ld * n) * es};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, dt, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 template <typename TIn, typename TOut, int BN, int STAGES, bool A_MN, bool B_MN, int CG>
-int launch_inst(pbx_handle_t h, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p) {
-  using Cfg = TcCfg<sizeof(TIn), BN, STAGES, CG>;
+int launch_inst(pbx_handle_t h, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                const TcParams& p) {
+  using Cfg = TcCfg<sizeof(TIn), BN, STAGES, CG, sizeof(TOut)>;
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared memory budget");
   auto kern = gemm_tc_kernel<TIn, TOut, BN, STAGES, A_MN, B_MN, CG>;
   PBX_CUDA_CHECK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -466,30 +536,30 @@ int launch_inst(pbx_handle_t h, const CUtensorMap& tmA, const CUtensorMap& tmB, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PBX_CUDA_CHECK(h, cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  PBX_CUDA_CHECK(h, cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, p));
   h->launches++;
   return PBX_OK;
 }
 
 template <typename TIn, typename TOut, int BN, int STAGES, int CG>
 int launch_major(pbx_handle_t h, bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                 const TcParams& p) {
+                 const CUtensorMap& tmC, const TcParams& p) {
   if (a_mn) {
-    return b_mn ? launch_inst<TIn, TOut, BN, STAGES, true, true, CG>(h, tmA, tmB, p)
-                : launch_inst<TIn, TOut, BN, STAGES, true, false, CG>(h, tmA, tmB, p);
+    return b_mn ? launch_inst<TIn, TOut, BN, STAGES, true, true, CG>(h, tmA, tmB, tmC, p)
+                : launch_inst<TIn, TOut, BN, STAGES, true, false, CG>(h, tmA, tmB, tmC, p);
   }
-  return b_mn ? launch_inst<TIn, TOut, BN, STAGES, false, true, CG>(h, tmA, tmB, p)
-              : launch_inst<TIn, TOut, BN, STAGES, false, false, CG>(h, tmA, tmB, p);
+  return b_mn ? launch_inst<TIn, TOut, BN, STAGES, false, true, CG>(h, tmA, tmB, tmC, p)
+              : launch_inst<TIn, TOut, BN, STAGES, false, false, CG>(h, tmA, tmB, tmC, p);
 }
 
 // tile configurations, most efficient first: CTA pair 256x256, CTA pair 256x128, single CTA 128x128
 template <typename TIn, typename TOut>
 int launch_cfg(pbx_handle_t h, int cg, int bn, bool a_mn, bool b_mn, const CUtensorMap& tmA,
-               const CUtensorMap& tmB, const TcParams& p) {
+               const CUtensorMap& tmB, const CUtensorMap& tmC, const TcParams& p) {
   constexpr bool F32 = sizeof(TIn) == 4;
-  if (cg == 2 && bn == 256) return launch_major<TIn, TOut, 256, F32 ? 3 : 6, 2>(h, a_mn, b_mn, tmA, tmB, p);
-  if (cg == 2) return launch_major<TIn, TOut, 128, F32 ? 4 : 8, 2>(h, a_mn, b_mn, tmA, tmB, p);
-  return launch_major<TIn, TOut, 128, F32 ? 3 : 6, 1>(h, a_mn, b_mn, tmA, tmB, p);
+  if (cg == 2 && bn == 256) return launch_major<TIn, TOut, 256, F32 ? 3 : 6, 2>(h, a_mn, b_mn, tmA, tmB, tmC, p);
+  if (cg == 2) return launch_major<TIn, TOut, 128, F32 ? 4 : 8, 2>(h, a_mn, b_mn, tmA, tmB, tmC, p);
+  return launch_major<TIn, TOut, 128, F32 ? 3 : 6, 1>(h, a_mn, b_mn, tmA, tmB, tmC, p);
 }
 
 struct TcPlan {
@@ -604,12 +674,23 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
   p.b_batched = (c.batch > 1 && c.sb > 0) ? 1 : 0;
   p.total_tiles = (int64_t)p.m_tiles * p.n_tiles * c.batch * slices;
 
+  // 16-bit C with beta == 0 leaves through shared memory + TMA stores when C is TMA-legal
+  CUtensorMap tmC = tmA;  // placeholder when unused (never dereferenced)
+  p.tma_store = 0;
+  const bool out16 = (c.dtype == PBX_F16 || c.dtype == PBX_BF16);
+  const char* ts_env = getenv("PBX_TMA_STORE");
+  if (out16 && c.beta == 0.0 && slices == 1 && !(ts_env && atoi(ts_env) == 0) && ((uintptr_t)c.C % 16 == 0) &&
+      (c.ldc * 2) % 16 == 0 && (c.batch == 1 || (c.sc * 2) % 16 == 0) && c.ldc * 2 < ((int64_t)1 << 40) &&
+      c.sc * 2 < ((int64_t)1 << 40)) {
+    if (make_c_map(&tmC, 2, dt, c.C, c.m, c.n, c.ldc, c.batch, c.sc)) p.tma_store = 1;
+  }
+
   switch (c.dtype) {
-    case PBX_F32: return launch_cfg<float, float>(h, cg, bn, a_mn, b_mn, tmA, tmB, p);
-    case PBX_F16: return launch_cfg<__half, __half>(h, cg, bn, a_mn, b_mn, tmA, tmB, p);
-    case PBX_F16_F32: return launch_cfg<__half, float>(h, cg, bn, a_mn, b_mn, tmA, tmB, p);
-    case PBX_BF16: return launch_cfg<__nv_bfloat16, __nv_bfloat16>(h, cg, bn, a_mn, b_mn, tmA, tmB, p);
-    case PBX_BF16_F32: return launch_cfg<__nv_bfloat16, float>(h, cg, bn, a_mn, b_mn, tmA, tmB, p);
+    case PBX_F32: return launch_cfg<float, float>(h, cg, bn, a_mn, b_mn, tmA, tmB, tmC, p);
+    case PBX_F16: return launch_cfg<__half, __half>(h, cg, bn, a_mn, b_mn, tmA, tmB, tmC, p);
+    case PBX_F16_F32: return launch_cfg<__half, float>(h, cg, bn, a_mn, b_mn, tmA, tmB, tmC, p);
+    case PBX_BF16: return launch_cfg<__nv_bfloat16, __nv_bfloat16>(h, cg, bn, a_mn, b_mn, tmA, tmB, tmC, p);
+    case PBX_BF16_F32: return launch_cfg<__nv_bfloat16, float>(h, cg, bn, a_mn, b_mn, tmA, tmB, tmC, p);
   }
   return PBX_ERR_INVALID_ARG;
 }

@@ -65,6 +65,9 @@ int pbx_destroy(pbx_handle_t h) {
   if (h->ws) cudaFree(h->ws);
   for (int i = 0; i < 3; ++i)
     if (h->stage[i]) cudaFree(h->stage[i]);
+  for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+  if (h->s_in) cudaStreamDestroy(h->s_in);
+  if (h->s_out) cudaStreamDestroy(h->s_out);
   delete h;
   return PBX_OK;
 }
@@ -377,55 +380,6 @@ int pbx_device_name(pbx_handle_t h, char* buf, int len) {
   cudaDeviceProp prop;
   PBX_CUDA_CHECK(h, cudaGetDeviceProperties(&prop, h->device));
   snprintf(buf, (size_t)len, "%s", prop.name);
-  return PBX_OK;
-}
-
-// ---- host-buffer path (end-to-end metric) ------------------------------------------------
-static int ensure_stage(pbx_handle_t h, int i, int64_t bytes) {
-  if (bytes <= h->stage_bytes[i]) return PBX_OK;
-  if (h->stage[i]) {
-    PBX_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
-    PBX_CUDA_CHECK(h, cudaFree(h->stage[i]));
-    h->stage[i] = nullptr; h->stage_bytes[i] = 0;
-  }
-  PBX_CUDA_CHECK(h, cudaMalloc(&h->stage[i], (size_t)bytes));
-  h->stage_bytes[i] = bytes;
-  return PBX_OK;
-}
-
-int pbx_gemm_host(pbx_handle_t h, int dtype, char transa, char transb, int64_t m, int64_t n,
-                  int64_t k, const void* alpha, const void* A_host, int64_t lda, int64_t stridea,
-                  const void* B_host, int64_t ldb, int64_t strideb, const void* beta, void* C_host,
-                  int64_t ldc, int64_t stridec, int64_t batch, int batch_type) {
-  if (!h || !valid_dtype(dtype) || !alpha || !beta || m < 0 || n < 0 || k < 0 || batch < 1)
-    return PBX_ERR_INVALID_ARG;
-  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
-  const bool ta = tolower((unsigned char)transa) != 'n', tb = tolower((unsigned char)transb) != 'n';
-  const int64_t a_cols = ta ? m : k, b_cols = tb ? k : n;
-  int64_t a_el, b_el, c_el;
-  if (batch_type == 1) {
-    a_el = lda * a_cols * batch; b_el = ldb * b_cols * batch; c_el = ldc * n * batch;
-  } else {
-    a_el = (batch - 1) * stridea + lda * a_cols;
-    b_el = (batch - 1) * strideb + ldb * b_cols;
-    c_el = (batch - 1) * stridec + ldc * n;
-  }
-  const int64_t a_bytes = a_el * (int64_t)pbx_in_size(dtype), b_bytes = b_el * (int64_t)pbx_in_size(dtype);
-  const int64_t c_bytes = c_el * (int64_t)pbx_out_size(dtype);
-  int st;
-  if ((st = ensure_stage(h, 0, a_bytes)) || (st = ensure_stage(h, 1, b_bytes)) ||
-      (st = ensure_stage(h, 2, c_bytes)))
-    return st;
-  const double be = read_scalar(dtype, beta);
-  PBX_CUDA_CHECK(h, cudaMemcpyAsync(h->stage[0], A_host, (size_t)a_bytes, cudaMemcpyHostToDevice, h->stream));
-  PBX_CUDA_CHECK(h, cudaMemcpyAsync(h->stage[1], B_host, (size_t)b_bytes, cudaMemcpyHostToDevice, h->stream));
-  if (be != 0.0 || ldc != m || (batch > 1 && batch_type == 0 && stridec != ldc * n))
-    PBX_CUDA_CHECK(h, cudaMemcpyAsync(h->stage[2], C_host, (size_t)c_bytes, cudaMemcpyHostToDevice, h->stream));
-  st = pbx_gemm(h, dtype, transa, transb, m, n, k, alpha, h->stage[0], lda, stridea, h->stage[1], ldb,
-                strideb, beta, h->stage[2], ldc, stridec, batch, batch_type);
-  if (st != PBX_OK) return st;
-  PBX_CUDA_CHECK(h, cudaMemcpyAsync(C_host, h->stage[2], (size_t)c_bytes, cudaMemcpyDeviceToHost, h->stream));
-  PBX_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
   return PBX_OK;
 }
 

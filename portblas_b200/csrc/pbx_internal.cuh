@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/pbx_gemm.h"
 
@@ -44,6 +45,9 @@ struct pbx_handle_s {
   // staging buffers for pbx_gemm_host
   void* stage[3] = {nullptr, nullptr, nullptr};
   int64_t stage_bytes[3] = {0, 0, 0};
+  // copy-in / copy-out streams and events of the pipelined host path (pbx_host.cu)
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  std::vector<cudaEvent_t> events;
 };
 
 #define PBX_CUDA_CHECK(h, expr)                                                          \

@@ -58,6 +58,20 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
+// smem tile -> global through a tensor map (clips rows / columns that fall outside the tensor)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int x, int y, int z) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+      ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(x), "r"(y), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// at most N of this thread's bulk groups may still be READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
 // ---- tcgen05 ---------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
@@ -140,9 +154,15 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t ran
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
-// arrive on a barrier that may live in the peer CTA (cluster-scope release)
+// arrive on a barrier that may live in the peer CTA (cluster-scope release: orders this thread's
+// prior shared-memory writes before the arrive for an observer in the other CTA)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// same, default (CTA-scope) semantics: enough when only tcgen05 / TMEM state is handed over (the
+// tcgen05.fence pair orders that) -- avoids the MEMBAR a cluster-scope release drains stores with
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // wait that observes arrivals from the peer CTA
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {

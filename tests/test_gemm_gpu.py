@@ -161,6 +161,19 @@ def test_strided_batched_tma_aligned(handle):
     assert run_case(handle, cases[0]).kernel == "tcgen05"
 
 
+def test_tma_store_and_direct_epilogues(handle):
+    """16-bit outputs with beta == 0 leave through shared memory + TMA stores when C is 16-byte legal;
+    the direct-store epilogue (PBX_TMA_STORE=0, or an odd ldc) must agree with it on ragged shapes."""
+    cases = []
+    for dt, env in itertools.product(("f16", "bf16"), ((("PBX_TMA_STORE", "1"),), (("PBX_TMA_STORE", "0"),))):
+        for m, n, ldc_mul, (ta, tb) in itertools.product([72, 200, 264], [40, 136, 300], [1, 2], TRANS):
+            cases.append(Case(dtype=dt, transa=ta, transb=tb, m=m, n=n, k=72, alpha=1.5, beta=0.0, ldc_mul=ldc_mul,
+                              kernel=TCGEN05, env=env))
+        cases.append(Case(dtype=dt, api="strided", m=136, n=72, k=64, alpha=1.0, beta=0.0, batch=7, stride_c_mul=3,
+                          kernel=TCGEN05, env=env))
+    _run_all(handle, cases)
+
+
 # ---- invalid arguments (gemm_interface.hpp:144-165) ------------------------------------------------
 def test_invalid_arguments(handle):
     cases = [Case(transa="x"), Case(transb="q"), Case(transa="c", transb="C"),
