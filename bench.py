@@ -30,15 +30,15 @@ WORKLOADS = {
     "dgemm8192": dict(dt="f64", m=8192, n=8192, k=8192, batch=1, ta="n", tb="n", alpha=1.0, beta=0.0,
                       desc="DGEMM 8192x8192x8192 NN alpha=1 beta=0 (BASELINE configs[1]); N>1: one such M-block per GPU"),
     # BASELINE configs[2] (per-GPU M-block of the 16384^3 problem when sharded 1/2/4/8 ways is 16384/N rows)
-    "sgemm16384": dict(dt="f32", m=16384, n=16384, k=16384, batch=1, ta="n", tb="n", alpha=1.0, beta=0.0,
-                       desc="SGEMM 16384^3 NN fp32 via 3xTF32 (BASELINE configs[2])"),
+    "sgemm16384": dict(dt="f32", m=16384, n=16384, k=16384, batch=1, ta="n", tb="n", alpha=1.0, beta=0.0, strong=True,
+                       desc="SGEMM 16384^3 NN fp32 via 3xTF32 (BASELINE configs[2]); N>1: M-block shards of the SAME problem"),
     "sgemm8192": dict(dt="f32", m=8192, n=8192, k=8192, batch=1, ta="n", tb="n", alpha=1.0, beta=0.0,
                       desc="SGEMM 8192^3 NN fp32 via 3xTF32"),
     # BASELINE configs[3]
-    "hgemm_batched": dict(dt="f16", m=256, n=256, k=256, batch=4096, ta="n", tb="n", alpha=1.0, beta=0.0,
-                          desc="strided-batched HGEMM, batch 4096 of 256^3 (BASELINE configs[3])"),
-    "bf16gemm_batched": dict(dt="bf16", m=256, n=256, k=256, batch=4096, ta="n", tb="n", alpha=1.0, beta=0.0,
-                             desc="strided-batched BF16 GEMM, batch 4096 of 256^3 (BASELINE configs[3])"),
+    "hgemm_batched": dict(dt="f16", m=256, n=256, k=256, batch=4096, ta="n", tb="n", alpha=1.0, beta=0.0, strong=True,
+                          desc="strided-batched HGEMM, batch 4096 of 256^3 (BASELINE configs[3]); N>1: batch shards of the SAME problem"),
+    "bf16gemm_batched": dict(dt="bf16", m=256, n=256, k=256, batch=4096, ta="n", tb="n", alpha=1.0, beta=0.0, strong=True,
+                             desc="strided-batched BF16 GEMM, batch 4096 of 256^3 (BASELINE configs[3]); N>1: batch shards of the SAME problem"),
     # BASELINE configs[4]
     "sgemm_splitk": dict(dt="f32", m=512, n=512, k=1048576, batch=1, ta="n", tb="n", alpha=1.0, beta=0.0,
                          desc="tall-skinny SGEMM M=N=512 K=1048576, split-K (BASELINE configs[4])"),
@@ -50,6 +50,7 @@ WORKLOADS = {
 }
 ES_IN = {"f64": 8, "f32": 4, "f16": 2, "bf16": 2}
 NOMINAL_FP64_TFLOPS = 40.0      # B200 datasheet FP64 (tensor == vector); MEASURED_PEAKS.json has no fp64 entry
+MEASURED_FP64_PIPE_TFLOPS = 36.98  # register-resident DMMA.8x8x4 loop on this pool's B200 (profiles/r01/dmma_rate.txt)
 NOMINAL_TF32_TFLOPS = 1100.0    # dense; the 3xTF32 roof is a third of the tf32 rate
 
 
@@ -76,7 +77,9 @@ def roofline_for(w, avg_ms, traffic):
     flops, byts = algorithmic(w)
     ai = flops / byts
     if w["dt"] == "f64":
-        tensor_peak, src = NOMINAL_FP64_TFLOPS, "nominal fp64 40 TF (no fp64 entry in MEASURED_PEAKS.json)"
+        tensor_peak = NOMINAL_FP64_TFLOPS
+        src = ("nominal fp64 40 TF (no fp64 entry in MEASURED_PEAKS.json); measured DMMA pipe ceiling "
+               f"{MEASURED_FP64_PIPE_TFLOPS} TF (tools/micro/dmma_rate.cu, profiles/r01/dmma_rate.txt)")
     elif w["dt"] == "f32":
         tensor_peak = pk["bf16"] / 2.0 / 3.0
         src = f"3xTF32 roof = bf16 {pk['source']} / 2 (tf32 rate) / 3 (three MMAs per product)"
@@ -260,12 +263,25 @@ def main():
     b = rand(ldb * n * batch)
     c = torch.zeros(ldc * n * batch, device=dev, dtype=tdt)
 
+    # N > 1.  weak: every rank runs the whole per-GPU shape on its own data.  strong (BASELINE configs[2],[3]):
+    # the SAME problem is cut into M-blocks / batch ranges (portblas_b200/sharding.py): a rank's shard is a
+    # pointer offset into the full operands with the ORIGINAL leading dimensions -- no copy, no collective.
+    strong = bool(w.get("strong")) and world > 1
+    m_loc, batch_loc, a_off, b_off, c_off = m, batch, 0, 0, 0
+    if strong and batch == 1:
+        sh = sharding.shard_mblock(w["ta"], m, lda, world, rank, align=256)
+        m_loc, a_off, c_off = sh.rows, sh.a_offset, sh.c_offset
+    elif strong:
+        bs = sharding.shard_batch(batch, m * k, k * n, m * n, world, rank)
+        batch_loc, a_off, b_off, c_off = bs.batches, bs.a_offset, bs.b_offset, bs.c_offset
+    a_v, b_v, c_v = a[a_off:], b[b_off:], c[c_off:]
+
     def step():
         if batch == 1:
-            blas._gemm(h, w["ta"], w["tb"], m, n, k, w["alpha"], a, lda, b, ldb, w["beta"], c, ldc)
+            blas._gemm(h, w["ta"], w["tb"], m_loc, n, k, w["alpha"], a_v, lda, b_v, ldb, w["beta"], c_v, ldc)
         else:
-            blas._gemm_strided_batched(h, w["ta"], w["tb"], m, n, k, w["alpha"], a, lda, m * k, b, ldb, k * n,
-                                       w["beta"], c, ldc, m * n, batch)
+            blas._gemm_strided_batched(h, w["ta"], w["tb"], m, n, k, w["alpha"], a_v, lda, m * k, b_v, ldb, k * n,
+                                       w["beta"], c_v, ldc, m * n, batch_loc)
 
     def barrier():
         if world > 1:
@@ -294,7 +310,8 @@ def main():
     total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
     flops, byts = algorithmic(w)
-    value = flops * world / (ms_per_step * 1e-3) / 1e12
+    job_flops = flops if strong else flops * world   # strong: the one problem; weak: one problem per GPU
+    value = job_flops / (ms_per_step * 1e-3) / 1e12
     kernel_used, split_used = h.last_kernel, h.last_split_k
 
     # ---- optional C gather (the only collective of the path) ----
@@ -304,8 +321,14 @@ def main():
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         dist.barrier()
         g0.record()
-        if batch == 1:
+        if batch == 1 and strong:
+            # compact (rows x n) copy of this rank's row block, then all-gather + interleave
+            c_loc = c.view(n, ldc)[:, c_off:c_off + m_loc].contiguous().view(-1)
+            full = sharding.gather_c_mblocks(c_loc, m, n, world, align=256)
+        elif batch == 1:
             full = sharding.gather_c_mblocks(c, m * world, n, world, align=m)
+        elif strong:
+            full = sharding.gather_c_batches(c_v[:batch_loc * m * n], m * n, batch, world)
         else:
             full = sharding.gather_c_batches(c, m * n, batch * world, world)
         g1.record()
@@ -325,9 +348,9 @@ def main():
         torch.cuda.synchronize()
 
         def e2e_step():
-            blas.gemm_host(h, w["ta"], w["tb"], m, n, k, w["alpha"], a_h, lda, b_h, ldb, w["beta"], c_h, ldc,
-                           stridea=m * k if batch > 1 else 0, strideb=k * n if batch > 1 else 0,
-                           stridec=m * n if batch > 1 else 0, batch_size=batch)
+            blas.gemm_host(h, w["ta"], w["tb"], m_loc, n, k, w["alpha"], a_h[a_off:], lda, b_h[b_off:], ldb, w["beta"],
+                           c_h[c_off:], ldc, stridea=m * k if batch > 1 else 0, strideb=k * n if batch > 1 else 0,
+                           stridec=m * n if batch > 1 else 0, batch_size=batch_loc)
         e2e_step()
         e2e_steps = max(1, min(args.steps, 5))
         barrier()
@@ -340,10 +363,12 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         el = float(te.item()) / e2e_steps
-        h2d = (a.numel() + b.numel()) * es + (c.numel() * es if w["beta"] != 0 else 0)
-        e2e = dict(value=round(flops * world / el / 1e12, 3), unit="TFLOP/s", h2d_bytes_per_step=int(h2d),
-                   d2h_bytes_per_step=int(c.numel() * es), ms_per_step=round(el * 1e3, 3), steps=e2e_steps,
-                   api="pbx_gemm_host (copy_to_device + _gemm + copy_to_host + wait), pinned host buffers")
+        c_el = m_loc * n * batch_loc
+        h2d = (m_loc * k * batch_loc + k * n * batch_loc) * es + (c_el * es if w["beta"] != 0 else 0)
+        e2e = dict(value=round(job_flops / el / 1e12, 3), unit="TFLOP/s", h2d_bytes_per_step=int(h2d),
+                   d2h_bytes_per_step=int(c_el * es), ms_per_step=round(el * 1e3, 3), steps=e2e_steps,
+                   api="pbx_gemm_host: pinned host buffers, H2D panels | GEMM | D2H panels pipelined on 3 streams "
+                       "(= copy_to_device + _gemm + copy_to_host + wait of samples/gemm.cpp)")
         del a_h, b_h, c_h
 
     if rank == 0:
@@ -352,16 +377,17 @@ def main():
         if tp.exists():
             traffic = json.loads(tp.read_text()).get(args.workload)
         avg_launch_ms = sum(per_launch) / len(per_launch)
-        roof = roofline_for(w, avg_launch_ms, traffic)
+        roof = roofline_for(dict(w, m=m_loc, batch=batch_loc), avg_launch_ms, traffic)  # rank 0's launch
         roof["kernel"] = kernel_used
         roof["avg_launch_ms"] = round(avg_launch_ms, 4)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_sample(w)
         line = dict(metric="gemm_tflops", value=round(value, 3), unit="TFLOP/s", n_gpus=world, steps=args.steps,
-                    warmup=args.warmup, ms_per_step=round(ms_per_step, 4), higher_is_better=True, scaling="weak",
+                    warmup=args.warmup, ms_per_step=round(ms_per_step, 4), higher_is_better=True,
+                    scaling="strong" if strong else "weak",
                     vs_baseline=None, dtype=w["dt"], data="synthetic U(-2,5), seed 12345+rank, generated on device",
-                    config=dict(workload=w["desc"], per_gpu_shape=[m, n, k, batch],
+                    config=dict(workload=w["desc"], per_gpu_shape=[m_loc, n, k, batch_loc],
                                 parallelism=f"mblock{world}" if batch == 1 else f"batchshard{world}",
                                 l2="inputs+output %.0f MiB per GPU > 126 MB L2, no flush needed" % (byts / 2**20)
                                 if byts > 200e6 else "working set fits L2: back-to-back launches reuse L2 (noted)",

@@ -277,7 +277,11 @@ __global__ void __launch_bounds__(DTHREADS, 1) gemm_dmma_kernel(DmmaParams p) {
 template <bool AK, bool BK_, int VEC>
 int launch_variant(pbx_handle_t h, const DmmaParams& p, dim3 grid) {
   auto kern = gemm_dmma_kernel<AK, BK_, VEC>;
-  PBX_CUDA_CHECK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DMMA_SMEM_BYTES));
+  static bool attr_set[16] = {};   // per device ordinal: the attribute is sticky, set it once
+  if (h->device >= 16 || !attr_set[h->device]) {
+    PBX_CUDA_CHECK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DMMA_SMEM_BYTES));
+    if (h->device < 16) attr_set[h->device] = true;
+  }
   kern<<<grid, DTHREADS, DMMA_SMEM_BYTES, h->stream>>>(p);
   h->launches++;
   PBX_CUDA_CHECK(h, cudaGetLastError());

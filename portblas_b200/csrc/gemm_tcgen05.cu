@@ -521,7 +521,11 @@ int launch_inst(pbx_handle_t h, const CUtensorMap& tmA, const CUtensorMap& tmB, 
   using Cfg = TcCfg<sizeof(TIn), BN, STAGES, CG, sizeof(TOut)>;
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared memory budget");
   auto kern = gemm_tc_kernel<TIn, TOut, BN, STAGES, A_MN, B_MN, CG>;
-  PBX_CUDA_CHECK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  static bool attr_set[16] = {};   // per device ordinal: the attribute is sticky, set it once
+  if (h->device >= 16 || !attr_set[h->device]) {
+    PBX_CUDA_CHECK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    if (h->device < 16) attr_set[h->device] = true;
+  }
   const int64_t units = h->sm_count / CG;   // persistent: one CTA (or CTA pair) per SM (pair)
   const int64_t groups = p.total_tiles < units ? p.total_tiles : units;
   cudaLaunchConfig_t cfg = {};
