@@ -199,6 +199,31 @@ __global__ void __launch_bounds__(256) gemm_interleaved_kernel(IlvParams p) {
   }
 }
 
+// ---- operand re-layout -----------------------------------------------------------
+// rows x cols column-major window (x batch) copied to a new leading dimension / batch stride, so
+// that an operand with an odd ld or a base that is not 16-byte aligned becomes TMA-legal.  One warp
+// per (column, 2048-row chunk): every load and store instruction covers 32 consecutive elements.
+template <typename T>
+__global__ void __launch_bounds__(256) repack_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t rows,
+                                                     int64_t cols, int64_t ld_s, int64_t ld_d, int64_t stride_s,
+                                                     int64_t stride_d, int64_t batch, int64_t chunks) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t units = batch * cols * chunks;
+  for (int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < units; u += nwarps) {
+    const int64_t chunk = u % chunks, col = (u / chunks) % cols, b = u / (chunks * cols);
+    const int64_t r0 = chunk * 2048, r1 = min(rows, r0 + 2048);
+    const T* s = src + b * stride_s + col * ld_s;
+    T* d = dst + b * stride_d + col * ld_d;
+    int64_t r = r0 + lane;
+    for (; r + 96 < r1; r += 128) {
+      const T v0 = s[r], v1 = s[r + 32], v2 = s[r + 64], v3 = s[r + 96];
+      d[r] = v0; d[r + 32] = v1; d[r + 64] = v2; d[r + 96] = v3;
+    }
+    for (; r < r1; r += 32) d[r] = s[r];
+  }
+}
+
 // ---- C <- beta*C ---------------------------------------------------------------
 template <typename TOut, typename TAcc>
 __global__ void __launch_bounds__(256) scal_matrix_kernel(TOut* C, int64_t m, int64_t n, int64_t ldc,
@@ -253,6 +278,27 @@ int dispatch_dtype(int dtype, F&& f) {
 }
 
 }  // namespace
+
+int pbx_launch_repack(pbx_handle_t h, int elem_bytes, const void* src, void* dst, int64_t rows, int64_t cols,
+                      int64_t ld_src, int64_t ld_dst, int64_t stride_src, int64_t stride_dst, int64_t batch) {
+  if (rows <= 0 || cols <= 0 || batch <= 0) return PBX_OK;
+  const int64_t chunks = (rows + 2047) / 2048;
+  const int64_t units = batch * cols * chunks;
+  int64_t blocks = (units + 7) / 8;   // 8 warps per block
+  const int64_t cap = (int64_t)h->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  if (elem_bytes == 2)
+    repack_kernel<uint16_t><<<(unsigned)blocks, 256, 0, h->stream>>>((const uint16_t*)src, (uint16_t*)dst, rows, cols,
+                                                                  ld_src, ld_dst, stride_src, stride_dst, batch, chunks);
+  else if (elem_bytes == 4)
+    repack_kernel<uint32_t><<<(unsigned)blocks, 256, 0, h->stream>>>((const uint32_t*)src, (uint32_t*)dst, rows, cols,
+                                                                  ld_src, ld_dst, stride_src, stride_dst, batch, chunks);
+  else
+    return PBX_ERR_INVALID_ARG;
+  h->launches++;
+  PBX_CUDA_CHECK(h, cudaGetLastError());
+  return PBX_OK;
+}
 
 int pbx_launch_simt(pbx_handle_t h, const PbxGemmCall& c, int slices) {
   SimtParams p;

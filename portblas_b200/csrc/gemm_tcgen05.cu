@@ -605,15 +605,18 @@ TcPlan make_plan(pbx_handle_t h, const PbxGemmCall& c) {
       }
     }
   }
-  // K slices: the reference splits by depth = ceil(4*CUs / tiles) when K > 2048
-  // (gemm_partial_local.hpp:191-199, portblas_handle.hpp:323); here: up to two waves of the machine.
+  // K slices.  The reference splits by depth = ceil(4*CUs / tiles) when K > 2048
+  // (gemm_partial_local.hpp:191-199, portblas_handle.hpp:323).  Here: when the output tiles cannot fill
+  // half of the SM (pairs), spread the K loop over up to two waves of them, but keep at least 4 K blocks
+  // (128 fp32 / 256 16-bit k) per slice and split only loops of >= 16 blocks: a lone CTA walks one
+  // K block per ~1 us (TMA -> MMA latency chain), the reduce epilogue costs one extra short launch.
   const Cand chosen = {plan.cg, plan.bn};
   const int64_t tiles = tiles_of(chosen), units = h->sm_count / plan.cg;
   int64_t slices = 1;
   if (h->forced_split_k > 1) slices = h->forced_split_k;
-  else if (h->forced_split_k == 0 && tiles * 2 <= units && c.k >= 2 * 2048) {
+  else if (h->forced_split_k == 0 && tiles * 2 <= units && kb >= 16) {
     slices = (2 * units) / tiles;
-    if (slices > c.k / 2048) slices = c.k / 2048;
+    if (slices > kb / 4) slices = kb / 4;
   }
   if (slices > kb) slices = kb;
   if (slices < 1) slices = 1;
@@ -624,18 +627,23 @@ TcPlan make_plan(pbx_handle_t h, const PbxGemmCall& c) {
 
 }  // namespace
 
-bool pbx_tcgen05_eligible(pbx_handle_t h, const PbxGemmCall& c) {
+bool pbx_tma_operand_ok(int dtype, const void* p, int64_t ld, int64_t stride) {
+  const int64_t es = (int64_t)pbx_in_size(dtype);
+  return ((uintptr_t)p % 16 == 0) && ((ld * es) % 16 == 0) && ((stride * es) % 16 == 0) &&
+         (ld * es < ((int64_t)1 << 40)) && (stride * es < ((int64_t)1 << 40));
+}
+
+bool pbx_tcgen05_shape_ok(pbx_handle_t h, const PbxGemmCall& c) {
   if (c.dtype == PBX_F64) return false;
-  const int64_t es = (int64_t)pbx_in_size(c.dtype);
-  auto ok = [&](const void* p, int64_t ld, int64_t stride) {
-    return ((uintptr_t)p % 16 == 0) && ((ld * es) % 16 == 0) && ((stride * es) % 16 == 0) &&
-           (ld * es < ((int64_t)1 << 40)) && (stride * es < ((int64_t)1 << 40));
-  };
-  if (!ok(c.A, c.lda, c.sa) || !ok(c.B, c.ldb, c.sb)) return false;
   if (c.m >= ((int64_t)1 << 31) || c.n >= ((int64_t)1 << 31) || c.k >= ((int64_t)1 << 31) ||
       c.batch >= ((int64_t)1 << 31))
     return false;
   return get_encode_fn() != nullptr;
+}
+
+bool pbx_tcgen05_eligible(pbx_handle_t h, const PbxGemmCall& c) {
+  return pbx_tcgen05_shape_ok(h, c) && pbx_tma_operand_ok(c.dtype, c.A, c.lda, c.sa) &&
+         pbx_tma_operand_ok(c.dtype, c.B, c.ldb, c.sb);
 }
 
 int pbx_tcgen05_slices(pbx_handle_t h, const PbxGemmCall& c) { return make_plan(h, c).slices; }

@@ -65,6 +65,8 @@ int pbx_destroy(pbx_handle_t h) {
   if (h->ws) cudaFree(h->ws);
   for (int i = 0; i < 3; ++i)
     if (h->stage[i]) cudaFree(h->stage[i]);
+  for (int i = 0; i < 2; ++i)
+    if (h->pack[i]) cudaFree(h->pack[i]);
   for (cudaEvent_t e : h->events) cudaEventDestroy(e);
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_out) cudaStreamDestroy(h->s_out);
@@ -86,6 +88,7 @@ int pbx_set_forced_kernel(pbx_handle_t h, int k) { if (!h) return PBX_ERR_INVALI
 int pbx_set_split_k(pbx_handle_t h, int s) { if (!h || s < 0) return PBX_ERR_INVALID_ARG; h->forced_split_k = s; return PBX_OK; }
 int pbx_last_kernel(pbx_handle_t h) { return h ? h->last_kernel : PBX_KERNEL_NONE; }
 int pbx_last_split_k(pbx_handle_t h) { return h ? h->last_split_k : 0; }
+int pbx_last_repack(pbx_handle_t h) { return h ? h->last_repack : 0; }
 int64_t pbx_launch_count(pbx_handle_t h) { return h ? h->launches : 0; }
 int64_t pbx_workspace_bytes(pbx_handle_t h) { return h ? h->ws_bytes : 0; }
 
@@ -140,21 +143,72 @@ static int choose_split_k(pbx_handle_t h, const PbxGemmCall& c, int tile_m, int 
   return slices;
 }
 
-static int run_gemm(pbx_handle_t h, const PbxGemmCall& c, int batch_type) {
+// An operand the TMA cannot address (odd leading dimension, base or batch stride off 16 bytes -- the
+// reference's offset / odd-ld test grids and many rows of its benchmark sweeps) is first copied to a
+// 16-byte-legal layout in a pooled buffer; the copy is one HBM-bound pass over that operand, after which
+// the call runs on the tensor cores instead of the CUDA-core kernel.
+static int ensure_pack(pbx_handle_t h, int i, int64_t bytes) {
+  if (bytes <= h->pack_bytes[i]) return PBX_OK;
+  if (h->pack[i]) {
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaFree(h->pack[i]) != cudaSuccess) return PBX_ERR_WORKSPACE;
+    h->pack[i] = nullptr; h->pack_bytes[i] = 0;
+  }
+  const int64_t rounded = ((bytes + (1 << 20) - 1) >> 20) << 20;
+  if (cudaMalloc(&h->pack[i], (size_t)rounded) != cudaSuccess) { cudaGetLastError(); return PBX_ERR_WORKSPACE; }
+  h->pack_bytes[i] = rounded;
+  return PBX_OK;
+}
+
+static bool repack_for_tma(pbx_handle_t h, PbxGemmCall& c) {
+  const int64_t es = (int64_t)pbx_in_size(c.dtype);
+  const int64_t quantum = 16 / es;
+  struct Op { const void** p; int64_t* ld; int64_t* st; int64_t rows, cols; };
+  Op ops[2] = {{&c.A, &c.lda, &c.sa, c.ta ? c.k : c.m, c.ta ? c.m : c.k},
+               {&c.B, &c.ldb, &c.sb, c.tb ? c.n : c.k, c.tb ? c.k : c.n}};
+  int mask = 0;
+  for (int i = 0; i < 2; ++i) {
+    Op& o = ops[i];
+    if (pbx_tma_operand_ok(c.dtype, *o.p, *o.ld, *o.st)) continue;
+    const int64_t ld2 = (o.rows + quantum - 1) / quantum * quantum;
+    const int64_t st2 = (*o.st > 0) ? ld2 * o.cols : 0;
+    const int64_t copies = (*o.st > 0) ? c.batch : 1;
+    const int64_t bytes = ld2 * o.cols * copies * es;
+    if (bytes > ((int64_t)16 << 30) || ensure_pack(h, i, bytes) != PBX_OK) return false;
+    if (pbx_launch_repack(h, (int)es, *o.p, h->pack[i], o.rows, o.cols, *o.ld, ld2, *o.st, st2, copies) != PBX_OK)
+      return false;
+    *o.p = h->pack[i]; *o.ld = ld2; *o.st = st2;
+    mask |= 1 << i;
+  }
+  h->last_repack = mask;
+  return true;
+}
+
+static int run_gemm(pbx_handle_t h, const PbxGemmCall& c_in, int batch_type) {
+  PbxGemmCall c = c_in;
   int kernel = h->forced_kernel;
+  h->last_repack = 0;
+  // tiny problems are launch-latency bound either way; the 128-row MMA tile wastes most of its lanes
+  // below ~32 rows, keep those on the CUDA-core kernel.
+  const bool tiny = (c.m * c.n < 64 * 64 && c.k < 4096);
+  // re-laying out an operand costs one pass over it: worth it once the contraction has real work
+  // (and a K loop deep enough to fill an MMA K block: below that the CUDA-core kernel reading in place wins)
+  const bool heavy = 2.0 * (double)c.m * (double)c.n * (double)c.k * (double)c.batch >= 5e7 && c.k >= 64;
   if (batch_type == 1 && c.batch > 1) {
     kernel = PBX_KERNEL_INTERLEAVED;
   } else if (kernel == PBX_KERNEL_AUTO || kernel == PBX_KERNEL_INTERLEAVED) {
     if (c.dtype == PBX_F64) {
       kernel = PBX_KERNEL_DMMA;
     } else if (pbx_tcgen05_eligible(h, c)) {
-      // tiny problems are launch-latency bound either way; the 128-row MMA tile wastes
-      // most of its lanes below ~32 rows, keep those on the CUDA-core kernel.
-      kernel = (c.m * c.n < 64 * 64 && c.k < 4096) ? PBX_KERNEL_SIMT : PBX_KERNEL_TCGEN05;
+      kernel = tiny ? PBX_KERNEL_SIMT : PBX_KERNEL_TCGEN05;
+    } else if (!tiny && heavy && pbx_tcgen05_shape_ok(h, c) && repack_for_tma(h, c)) {
+      kernel = PBX_KERNEL_TCGEN05;
     } else {
       kernel = PBX_KERNEL_SIMT;
     }
   }
+  if (kernel == PBX_KERNEL_TCGEN05 && c.dtype != PBX_F64 && !pbx_tcgen05_eligible(h, c) &&
+      pbx_tcgen05_shape_ok(h, c))
+    repack_for_tma(h, c);   // forced tensor-core path on an unaligned operand
   if (kernel == PBX_KERNEL_TCGEN05 && (c.dtype == PBX_F64 || !pbx_tcgen05_eligible(h, c)))
     kernel = (c.dtype == PBX_F64) ? PBX_KERNEL_DMMA : PBX_KERNEL_SIMT;
   if (kernel == PBX_KERNEL_DMMA && c.dtype != PBX_F64) kernel = PBX_KERNEL_SIMT;

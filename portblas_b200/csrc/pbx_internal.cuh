@@ -37,11 +37,15 @@ struct pbx_handle_s {
   int forced_split_k = 0;
   int last_kernel = PBX_KERNEL_NONE;
   int last_split_k = 1;
+  int last_repack = 0;
   int64_t launches = 0;
   std::string last_error;
   // split-K workspace pool (stream ordered; grows monotonically)
   void* ws = nullptr;
   int64_t ws_bytes = 0;
+  // aligned copies of TMA-illegal operands (pbx_api.cu: repack_for_tma); grow monotonically
+  void* pack[2] = {nullptr, nullptr};
+  int64_t pack_bytes[2] = {0, 0};
   // staging buffers for pbx_gemm_host
   void* stage[3] = {nullptr, nullptr, nullptr};
   int64_t stage_bytes[3] = {0, 0, 0};
@@ -88,6 +92,11 @@ int pbx_launch_scal(pbx_handle_t h, int dtype, int64_t m, int64_t n, double beta
                     int64_t ldc, int64_t stridec, int64_t batch, int interleaved);
 int pbx_launch_splitk_reduce(pbx_handle_t h, const PbxGemmCall& c, int slices);
 bool pbx_tcgen05_eligible(pbx_handle_t h, const PbxGemmCall& c);
+bool pbx_tcgen05_shape_ok(pbx_handle_t h, const PbxGemmCall& c);   // everything except operand alignment
+bool pbx_tma_operand_ok(int dtype, const void* p, int64_t ld, int64_t stride);
+// copy a rows x cols column-major window (x batch) to a new leading dimension / batch stride
+int pbx_launch_repack(pbx_handle_t h, int elem_bytes, const void* src, void* dst, int64_t rows, int64_t cols,
+                      int64_t ld_src, int64_t ld_dst, int64_t stride_src, int64_t stride_dst, int64_t batch);
 int pbx_tcgen05_slices(pbx_handle_t h, const PbxGemmCall& c);  // K slices the tcgen05 plan wants
 int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices);
 int pbx_launch_dmma(pbx_handle_t h, const PbxGemmCall& c, int slices);

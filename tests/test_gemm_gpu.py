@@ -210,6 +210,33 @@ def test_split_k_auto_selected(handle):
     assert r.kernel == "tcgen05" and r.split_k > 1, r
 
 
+def test_split_k_mid_k_few_tiles(handle):
+    """CNN-style rows of the reference sweeps (benchmark/config_csv/blas3/gemm/*im2col*): one or two output tiles
+    with K of a few thousand must not leave 140 SMs idle behind a single CTA's latency-bound K loop."""
+    for dt, m, n, k in [("f32", 128, 128, 3136), ("f32", 64, 64, 784), ("bf16", 256, 196, 2304), ("f16f32", 64, 576, 3072)]:
+        r = run_case(handle, Case(dtype=dt, m=m, n=n, k=k, alpha=1.0, beta=0.0))
+        assert r.ok, r
+        assert r.kernel == "tcgen05" and r.split_k > 1, (dt, m, n, k, r)
+
+
+def test_unaligned_operands_repacked_to_tensor_cores(handle):
+    """Odd leading dimensions / element offsets (the reference's OffsetNonZero and LD-multiplied grids, and e.g.
+    64x147x423200 of its ResNet sweep) cannot be addressed by TMA: the operand is re-laid out once and the call
+    still runs on tcgen05."""
+    cases = []
+    for dt in ("f32", "f16", "bf16f32"):
+        for (ta, tb), off in itertools.product(TRANS, [1, 33]):
+            cases.append(Case(dtype=dt, transa=ta, transb=tb, m=261, n=259, k=517, alpha=1.5, beta=0.5, offset=off))
+        cases.append(Case(dtype=dt, api="strided", m=131, n=67, k=129, batch=5, stride_a_mul=0, stride_b_mul=2,
+                          offset=3, alpha=1.0, beta=0.0))
+        cases.append(Case(dtype=dt, api="strided", transa="t", transb="t", m=131, n=67, k=129, batch=5, stride_a_mul=2,
+                          stride_b_mul=0, offset=3, alpha=1.0, beta=1.0))
+    _run_all(handle, cases)
+    r = run_case(handle, cases[0])
+    assert r.kernel == "tcgen05", r
+    assert handle.last_repack == 3
+
+
 # ---- JointMatrix-style grid (test/unittest/joint_matrix/*.cpp): narrow-compute numerics ---------------
 @pytest.mark.parametrize("dt", ["f16f32", "bf16f32", "f16"])
 def test_joint_matrix_grid(handle, dt):

@@ -40,6 +40,9 @@ def main():
     ap.add_argument("--api", default="gemm,gemm_batched,gemm_batched_strided")
     ap.add_argument("--max-rows", type=int, default=0)
     ap.add_argument("--max-gib", type=float, default=60.0)
+    ap.add_argument("--graph", action="store_true",
+                    help="time CUDA-graph replays of the call (device time without the Python/ctypes launch cost, "
+                         "which is ~20 us per call and hides every small shape)")
     args = ap.parse_args()
     rows = json.loads((ROOT / "tests" / "golden" / "config_csv_shapes.json").read_text())["rows"]
     rows = [r for r in rows if r["api"] in args.api.split(",")]
@@ -47,6 +50,7 @@ def main():
         rows = rows[:args.max_rows]
     dev = torch.device("cuda", 0)
     h = SB_Handle(0)
+    side = torch.cuda.Stream(device=dev)
     dt = TDT[args.dtype]
     es = torch.empty(0, dtype=dt).element_size()
     gen = torch.Generator(device=dev)
@@ -119,13 +123,32 @@ def main():
         for _ in range(2):
             run()
         torch.cuda.synchronize()
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
-        evs[0].record()
-        for i in range(iters):
-            run()
-            evs[i + 1].record()
-        torch.cuda.synchronize()
-        ts = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(iters))
+        if args.graph:
+            reps = 1 if flops > 5e10 else 8
+            h.set_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                for _ in range(reps):
+                    run()
+            h.set_stream(torch.cuda.current_stream(dev))
+            graph.replay()
+            torch.cuda.synchronize()
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+            evs[0].record()
+            for i in range(iters):
+                graph.replay()
+                evs[i + 1].record()
+            torch.cuda.synchronize()
+            ts = sorted(evs[i].elapsed_time(evs[i + 1]) / reps for i in range(iters))
+            del graph
+        else:
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+            evs[0].record()
+            for i in range(iters):
+                run()
+                evs[i + 1].record()
+            torch.cuda.synchronize()
+            ts = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(iters))
         ms = ts[len(ts) // 2]
         byts = (m * k + k * n + m * n * (2 if r["beta"] != 0 else 1)) * es * batch
         ai = flops / byts
@@ -134,7 +157,7 @@ def main():
         print(json.dumps(dict(base, kernel=kernel, split_k=split_k, ms=round(ms, 4), tflops=round(tf, 2),
                               gbs=round(byts / ms / 1e6, 1), ai=round(ai, 1),
                               bound="hbm" if ai * HBM_GBS / 1e3 < PEAK_TF[args.dtype] else "tensor",
-                              frac_of_roof=round(tf / roof_tf, 3), max_rel_err=float(f"{worst:.3e}"), ok=ok)), flush=True)
+                              frac_of_roof=round(tf / roof_tf, 3), timing="graph" if args.graph else "launch", repack=h.last_repack, max_rel_err=float(f"{worst:.3e}"), ok=ok)), flush=True)
         del a, b, c, c0
         if ilv:
             del a_i, b_i, c_i
