@@ -71,28 +71,46 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(SimtParams p) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = TAcc(0);
 
-    for (int64_t k0 = kbeg; k0 < kend; k0 += SBK) {
+    // global -> registers for K block k0 (issued one block ahead, so the loads fly under the FMAs)
+    TAcc ra[4], rb[4];
+    auto gload = [&](int64_t k0) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int e = tid + i * 256;
         int mm, kk;
         if (a_mcontig) { mm = e % SBM; kk = e / SBM; } else { kk = e % SBK; mm = e / SBK; }
-        TAcc v = TAcc(0);
+        ra[i] = TAcc(0);
         if (m0 + mm < p.m && k0 + kk < kend)
-          v = (TAcc)Cvt<TIn>::to_f(A[(m0 + mm) * p.a_rs + (k0 + kk) * p.a_cs]);
-        As[kk][mm] = v;
+          ra[i] = (TAcc)Cvt<TIn>::to_f(A[(m0 + mm) * p.a_rs + (k0 + kk) * p.a_cs]);
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int e = tid + i * 256;
         int nn, kk;
         if (b_kcontig) { kk = e % SBK; nn = e / SBK; } else { nn = e % SBN; kk = e / SBN; }
-        TAcc v = TAcc(0);
+        rb[i] = TAcc(0);
         if (n0 + nn < p.n && k0 + kk < kend)
-          v = (TAcc)Cvt<TIn>::to_f(B[(k0 + kk) * p.b_rs + (n0 + nn) * p.b_cs]);
-        Bs[kk][nn] = v;
+          rb[i] = (TAcc)Cvt<TIn>::to_f(B[(k0 + kk) * p.b_rs + (n0 + nn) * p.b_cs]);
+      }
+    };
+    gload(kbeg);
+    for (int64_t k0 = kbeg; k0 < kend; k0 += SBK) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int e = tid + i * 256;
+        int mm, kk;
+        if (a_mcontig) { mm = e % SBM; kk = e / SBM; } else { kk = e % SBK; mm = e / SBK; }
+        As[kk][mm] = ra[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int e = tid + i * 256;
+        int nn, kk;
+        if (b_kcontig) { kk = e % SBK; nn = e / SBK; } else { nn = e % SBN; kk = e / SBN; }
+        Bs[kk][nn] = rb[i];
       }
       __syncthreads();
+      if (k0 + SBK < kend) gload(k0 + SBK);
 #pragma unroll
       for (int kk = 0; kk < SBK; ++kk) {
         TAcc a[4], bb[4];
@@ -170,14 +188,38 @@ __global__ void __launch_bounds__(256) gemm_interleaved_kernel(IlvParams p) {
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = TAcc(0);
-    for (int64_t kk = 0; kk < p.k; ++kk) {
+    // rows / columns past the edge are clamped (their results are never stored): every load is
+    // unconditional, so four K steps' worth (32 loads) can be in flight per thread
+    int64_t a_off[4], b_off[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a_off[i] = min(m0 + i, p.m - 1) * p.a_rs * p.batch;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b_off[j] = min(n0 + j, p.n - 1) * p.b_cs * p.batch;
+    const int64_t a_kstep = p.a_cs * p.batch, b_kstep = p.b_rs * p.batch;
+    int64_t kk = 0;
+    for (; kk + 4 <= p.k; kk += 4) {
+      TIn av[4][4], bv[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) av[u][i] = A[a_off[i] + (kk + u) * a_kstep];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bv[u][j] = B[b_off[j] + (kk + u) * b_kstep];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            acc[i][j] = fma((TAcc)Cvt<TIn>::to_f(av[u][i]), (TAcc)Cvt<TIn>::to_f(bv[u][j]), acc[i][j]);
+    }
+    for (; kk < p.k; ++kk) {
       TAcc a[4], bb[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        a[i] = (m0 + i < p.m) ? (TAcc)Cvt<TIn>::to_f(A[((m0 + i) * p.a_rs + kk * p.a_cs) * p.batch]) : TAcc(0);
+      for (int i = 0; i < 4; ++i) a[i] = (TAcc)Cvt<TIn>::to_f(A[a_off[i] + kk * a_kstep]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        bb[j] = (n0 + j < p.n) ? (TAcc)Cvt<TIn>::to_f(B[(kk * p.b_rs + (n0 + j) * p.b_cs) * p.batch]) : TAcc(0);
+      for (int j = 0; j < 4; ++j) bb[j] = (TAcc)Cvt<TIn>::to_f(B[b_off[j] + kk * b_kstep]);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll

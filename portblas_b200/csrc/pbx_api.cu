@@ -189,10 +189,11 @@ static int run_gemm(pbx_handle_t h, const PbxGemmCall& c_in, int batch_type) {
   h->last_repack = 0;
   // tiny problems are launch-latency bound either way; the 128-row MMA tile wastes most of its lanes
   // below ~32 rows, keep those on the CUDA-core kernel.
-  const bool tiny = (c.m * c.n < 64 * 64 && c.k < 4096);
+  const double flops = 2.0 * (double)c.m * (double)c.n * (double)c.k * (double)c.batch;
+  const bool tiny = flops < 4e6 || (c.m * c.n < 64 * 64 && c.k < 256);
   // re-laying out an operand costs one pass over it: worth it once the contraction has real work
   // (and a K loop deep enough to fill an MMA K block: below that the CUDA-core kernel reading in place wins)
-  const bool heavy = 2.0 * (double)c.m * (double)c.n * (double)c.k * (double)c.batch >= 5e7 && c.k >= 64;
+  const bool heavy = c.k >= 64;
   if (batch_type == 1 && c.batch > 1) {
     kernel = PBX_KERNEL_INTERLEAVED;
   } else if (kernel == PBX_KERNEL_AUTO || kernel == PBX_KERNEL_INTERLEAVED) {
@@ -222,7 +223,7 @@ static int run_gemm(pbx_handle_t h, const PbxGemmCall& c_in, int batch_type) {
   const size_t acc_size = (c.dtype == PBX_F64) ? 8 : 4;
   if (kernel == PBX_KERNEL_TCGEN05) slices = pbx_tcgen05_slices(h, c);
   else if (kernel == PBX_KERNEL_DMMA) slices = choose_split_k(h, c, 128, 128, 16, 1024);
-  else slices = choose_split_k(h, c, 64, 64, 16, 1024);
+  else slices = choose_split_k(h, c, 64, 64, 16, 256);
   if (slices > 1) {
     st = pbx_ensure_workspace(h, (int64_t)acc_size * c.m * c.n * c.batch * slices);
     if (st != PBX_OK) return st;
