@@ -12,6 +12,8 @@
 //                              src/sb_handle/portblas_handle.hpp:354-398).
 #include <stdio.h>
 
+#include <stdlib.h>
+
 #include "pbx_internal.cuh"
 
 namespace {
@@ -171,7 +173,7 @@ struct IlvParams {
   double alpha, beta;
 };
 
-template <typename TIn, typename TOut, typename TAcc>
+template <typename TIn, typename TOut, typename TAcc, int UNROLL>
 __global__ void __launch_bounds__(256) gemm_interleaved_kernel(IlvParams p) {
   // one thread = one batch entry x one 4x4 output tile; consecutive threads walk the batch
   // index, which is the contiguous dimension of the interleaved layout.
@@ -197,22 +199,27 @@ __global__ void __launch_bounds__(256) gemm_interleaved_kernel(IlvParams p) {
     for (int j = 0; j < 4; ++j) b_off[j] = min(n0 + j, p.n - 1) * p.b_cs * p.batch;
     const int64_t a_kstep = p.a_cs * p.batch, b_kstep = p.b_rs * p.batch;
     int64_t kk = 0;
-    for (; kk + 4 <= p.k; kk += 4) {
-      TIn av[4][4], bv[4][4];
+    for (; kk + UNROLL <= p.k; kk += UNROLL) {
+      TIn av[UNROLL][4], bv[UNROLL][4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) av[u][i] = A[a_off[i] + (kk + u) * a_kstep];
 #pragma unroll
         for (int j = 0; j < 4; ++j) bv[u][j] = B[b_off[j] + (kk + u) * b_kstep];
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < UNROLL; ++u) {
+        TAcc a[4], bb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = (TAcc)Cvt<TIn>::to_f(av[u][i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bb[j] = (TAcc)Cvt<TIn>::to_f(bv[u][j]);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            acc[i][j] = fma((TAcc)Cvt<TIn>::to_f(av[u][i]), (TAcc)Cvt<TIn>::to_f(bv[u][j]), acc[i][j]);
+          for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], bb[j], acc[i][j]);
+      }
     }
     for (; kk < p.k; ++kk) {
       TAcc a[4], bb[4];
@@ -385,7 +392,12 @@ int pbx_launch_interleaved(pbx_handle_t h, const PbxGemmCall& c) {
     using TIn = std::remove_pointer_t<decltype(ti)>;
     using TOut = std::remove_pointer_t<decltype(to)>;
     using TAcc = std::remove_pointer_t<decltype(ta)>;
-    gemm_interleaved_kernel<TIn, TOut, TAcc><<<(unsigned)blocks, 256, 0, h->stream>>>(p);
+    // K steps whose loads are issued together (in-flight loads per thread = 8 x unroll)
+    static const int env_unroll = getenv("PBX_ILV_UNROLL") ? atoi(getenv("PBX_ILV_UNROLL")) : 0;
+    const int unroll = env_unroll ? env_unroll : 4;
+    if (unroll >= 4) gemm_interleaved_kernel<TIn, TOut, TAcc, 4><<<(unsigned)blocks, 256, 0, h->stream>>>(p);
+    else if (unroll >= 2) gemm_interleaved_kernel<TIn, TOut, TAcc, 2><<<(unsigned)blocks, 256, 0, h->stream>>>(p);
+    else gemm_interleaved_kernel<TIn, TOut, TAcc, 1><<<(unsigned)blocks, 256, 0, h->stream>>>(p);
     h->launches++;
     PBX_CUDA_CHECK(h, cudaGetLastError());
     return PBX_OK;

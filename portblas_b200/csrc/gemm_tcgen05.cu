@@ -21,6 +21,11 @@
 // D (128 x BN fp32) sits in TMEM with row m on lane m, so a warp's 32 lanes hold 32
 // consecutive rows of one column: stores to column-major C are fully coalesced.
 //
+// Skinny M (M <= 64 < N): the roles of the operands are swapped -- the kernel computes
+// C^T = op(B)^T op(A)^T, so N rides on the 128 TMEM lanes and M on a 64-wide MMA N dimension (half the
+// tensor-pipe time of a 128-row tile that is mostly zero padding).  Only the descriptors and the
+// epilogue addressing change (TRANS_OUT): a thread then owns 32 CONSECUTIVE elements of a C column.
+//
 // fp32 (3xTF32): a = hi + lo with hi = tf32(a), lo = tf32(a - hi);
 //   D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi   (fp32 accumulate, lo*lo dropped: ~2^-22 relative)
 // The tensor core adds into its fp32 accumulator with truncation, a one-sided error that grows
@@ -52,6 +57,7 @@ struct TcParams {
   int raw_hi;        // fp32: 1 = feed raw fp32 as the hi operand (hardware truncates to tf32)
   int a_batched, b_batched;
   int tma_store;     // 16-bit C through shared memory + TMA store (needs beta == 0, aligned C, no split-K)
+  int c_vec;         // TRANS_OUT: C rows of 32 elements may be stored as 16-byte vectors
   int64_t total_tiles;
 };
 
@@ -123,7 +129,9 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int64_t tile
   return c;
 }
 
-template <typename TIn, typename TOut, int BN, int STAGES, bool A_MN, bool B_MN, int CG>
+// M, N, ldc in TcParams are the KERNEL's view: with TRANS_OUT the caller passed (N, M) and the kernel's
+// D(row r, column c) is C(c, r), i.e. element address c + r*ldc instead of r + c*ldc.
+template <typename TIn, typename TOut, int BN, int STAGES, bool A_MN, bool B_MN, int CG, bool TRANS_OUT>
 __global__ void __launch_bounds__(TcCfg<sizeof(TIn), BN, STAGES, CG, sizeof(TOut)>::NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const TcParams p) {
@@ -332,7 +340,60 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             continue;
           }
           const bool full = rows_full && (n0 + c0 + 32 <= p.N);   // warp-uniform: no predicate per element
-          if (p.slices > 1) {
+          if (TRANS_OUT) {
+            // kernel row (lane) = column of C, kernel columns = 32 consecutive rows of C
+            const int64_t cc = n0 + c0;
+            if (p.slices > 1) {
+              float* ws = p.ws + (((int64_t)tc.b * p.slices + tc.slice) * p.M + m) * p.N + cc;
+              if (full && (p.N & 3) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<float4*>(ws + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                   __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (m_ok && cc + j < p.N) ws[j] = __uint_as_float(v[j]);
+              }
+            } else if (OUT16 && tma_store) {
+              const uint32_t buf = store_blk & 1u;
+              ++store_blk;
+              if (lane == 0) bulk_wait_read<1>();
+              __syncwarp();
+              TOut* st = stage_ptr + buf * (Cfg::EPI_TILE_BYTES / (int)sizeof(TOut)) + lane * 32;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) OutCvt<TOut>::store(st + j, p.alpha * __uint_as_float(v[j]));
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_3d(&tmC, stage_u32 + buf * Cfg::EPI_TILE_BYTES, (int)cc, (int)m_warp, tc.b);
+                bulk_commit();
+              }
+            } else {
+              TOut* dst = reinterpret_cast<TOut*>(p.C) + (int64_t)tc.b * p.sc + m * p.ldc + cc;
+              if (full && p.c_vec && sizeof(TOut) == 4) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  float4 o = make_float4(p.alpha * __uint_as_float(v[j]), p.alpha * __uint_as_float(v[j + 1]),
+                                         p.alpha * __uint_as_float(v[j + 2]), p.alpha * __uint_as_float(v[j + 3]));
+                  if (!beta0) {
+                    const float4 ci = *reinterpret_cast<const float4*>(dst + j);
+                    o.x += p.beta * ci.x; o.y += p.beta * ci.y; o.z += p.beta * ci.z; o.w += p.beta * ci.w;
+                  }
+                  *reinterpret_cast<float4*>(dst + j) = o;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  if (m_ok && cc + j < p.N) {
+                    float r = p.alpha * __uint_as_float(v[j]);
+                    if (!beta0) r += p.beta * OutCvt<TOut>::load(dst + j);
+                    OutCvt<TOut>::store(dst + j, r);
+                  }
+                }
+              }
+            }
+          } else if (p.slices > 1) {
             float* ws = p.ws + (((int64_t)tc.b * p.slices + tc.slice) * p.N + (n0 + c0)) * p.M + m;
             if (full) {
 #pragma unroll
@@ -515,12 +576,12 @@ bool make_c_map(CUtensorMap* out, int es, CUtensorMapDataType dt, void* ptr, int
   return r == CUDA_SUCCESS;
 }
 
-template <typename TIn, typename TOut, int BN, int STAGES, bool A_MN, bool B_MN, int CG>
+template <typename TIn, typename TOut, int BN, int STAGES, bool A_MN, bool B_MN, int CG, bool TRANS_OUT>
 int launch_inst(pbx_handle_t h, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                 const TcParams& p) {
   using Cfg = TcCfg<sizeof(TIn), BN, STAGES, CG, sizeof(TOut)>;
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared memory budget");
-  auto kern = gemm_tc_kernel<TIn, TOut, BN, STAGES, A_MN, B_MN, CG>;
+  auto kern = gemm_tc_kernel<TIn, TOut, BN, STAGES, A_MN, B_MN, CG, TRANS_OUT>;
   static bool attr_set[16] = {};   // per device ordinal: the attribute is sticky, set it once
   if (h->device >= 16 || !attr_set[h->device]) {
     PBX_CUDA_CHECK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -545,22 +606,24 @@ int launch_inst(pbx_handle_t h, const CUtensorMap& tmA, const CUtensorMap& tmB, 
   return PBX_OK;
 }
 
-template <typename TIn, typename TOut, int BN, int STAGES, int CG>
+template <typename TIn, typename TOut, int BN, int STAGES, int CG, bool TRANS_OUT = false>
 int launch_major(pbx_handle_t h, bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB,
                  const CUtensorMap& tmC, const TcParams& p) {
   if (a_mn) {
-    return b_mn ? launch_inst<TIn, TOut, BN, STAGES, true, true, CG>(h, tmA, tmB, tmC, p)
-                : launch_inst<TIn, TOut, BN, STAGES, true, false, CG>(h, tmA, tmB, tmC, p);
+    return b_mn ? launch_inst<TIn, TOut, BN, STAGES, true, true, CG, TRANS_OUT>(h, tmA, tmB, tmC, p)
+                : launch_inst<TIn, TOut, BN, STAGES, true, false, CG, TRANS_OUT>(h, tmA, tmB, tmC, p);
   }
-  return b_mn ? launch_inst<TIn, TOut, BN, STAGES, false, true, CG>(h, tmA, tmB, tmC, p)
-              : launch_inst<TIn, TOut, BN, STAGES, false, false, CG>(h, tmA, tmB, tmC, p);
+  return b_mn ? launch_inst<TIn, TOut, BN, STAGES, false, true, CG, TRANS_OUT>(h, tmA, tmB, tmC, p)
+              : launch_inst<TIn, TOut, BN, STAGES, false, false, CG, TRANS_OUT>(h, tmA, tmB, tmC, p);
 }
 
-// tile configurations, most efficient first: CTA pair 256x256, CTA pair 256x128, single CTA 128x128
+// tile configurations, most efficient first: CTA pair 256x256, CTA pair 256x128, single CTA 128x128;
+// bn == 64 is the skinny-M configuration (operands swapped, 128 columns of C x 64 rows per tile)
 template <typename TIn, typename TOut>
 int launch_cfg(pbx_handle_t h, int cg, int bn, bool a_mn, bool b_mn, const CUtensorMap& tmA,
                const CUtensorMap& tmB, const CUtensorMap& tmC, const TcParams& p) {
   constexpr bool F32 = sizeof(TIn) == 4;
+  if (bn == 64) return launch_major<TIn, TOut, 64, F32 ? 4 : 8, 1, true>(h, a_mn, b_mn, tmA, tmB, tmC, p);  // swapped operands
   if (cg == 2 && bn == 256) return launch_major<TIn, TOut, 256, F32 ? 3 : 6, 2>(h, a_mn, b_mn, tmA, tmB, tmC, p);
   if (cg == 2) return launch_major<TIn, TOut, 128, F32 ? 4 : 8, 2>(h, a_mn, b_mn, tmA, tmB, tmC, p);
   return launch_major<TIn, TOut, 128, F32 ? 3 : 6, 1>(h, a_mn, b_mn, tmA, tmB, tmC, p);
@@ -568,6 +631,7 @@ int launch_cfg(pbx_handle_t h, int cg, int bn, bool a_mn, bool b_mn, const CUten
 
 struct TcPlan {
   int cg, bn, slices;
+  bool swap;   // compute C^T = op(B)^T op(A)^T (skinny M)
 };
 
 // Shape -> {cta_group, tile width, K slices}.  Replaces the reference's NVIDIA heuristics
@@ -582,11 +646,15 @@ TcPlan make_plan(pbx_handle_t h, const PbxGemmCall& c) {
     return ((c.m + 128 * cd.cg - 1) / (128 * cd.cg)) * ((c.n + cd.bn - 1) / cd.bn) * c.batch;
   };
   auto usable = [&](const Cand& cd) { return !(cd.cg == 2 && c.m <= 128) && !(cd.bn == 256 && c.n <= 128); };
-  TcPlan plan = {1, 128, 1};
+  TcPlan plan = {1, 128, 1, false};
+  const char* swap_env = getenv("PBX_TC_SWAP");   // "0" disables the skinny-M operand swap (testing)
+  const bool want_swap = c.m <= 64 && c.n > c.m && !(swap_env && atoi(swap_env) == 0);
   const char* force = getenv("PBX_TC_CONFIG");  // "cg,bn" (testing)
   int fcg = 0, fbn = 0;
   if (force && sscanf(force, "%d,%d", &fcg, &fbn) == 2 && (fcg == 1 || fcg == 2) && (fbn == 128 || (fbn == 256 && fcg == 2))) {
     plan.cg = fcg; plan.bn = fbn;
+  } else if (want_swap) {
+    plan.cg = 1; plan.bn = 64; plan.swap = true;
   } else {
     bool found = false;
     for (const Cand& cd : cands) {
@@ -611,7 +679,7 @@ TcPlan make_plan(pbx_handle_t h, const PbxGemmCall& c) {
   // (128 fp32 / 256 16-bit k) per slice and split only loops of >= 16 blocks: a lone CTA walks one
   // K block per ~1 us (TMA -> MMA latency chain), the reduce epilogue costs one extra short launch.
   const Cand chosen = {plan.cg, plan.bn};
-  const int64_t tiles = tiles_of(chosen), units = h->sm_count / plan.cg;
+  const int64_t tiles = plan.swap ? ((c.n + 127) / 128) * c.batch : tiles_of(chosen), units = h->sm_count / plan.cg;
   int64_t slices = 1;
   if (h->forced_split_k > 1) slices = h->forced_split_k;
   else if (h->forced_split_k == 0 && tiles * 2 <= units && kb >= 16) {
@@ -655,23 +723,28 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
   TcPlan plan = make_plan(h, c);
   plan.slices = slices;
   const int bn = plan.bn, cg = plan.cg;
-  const bool a_mn = !c.ta, b_mn = c.tb;
   CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                : ((c.dtype == PBX_F16 || c.dtype == PBX_F16_F32) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
                                                                                 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  // The kernel's operands.  Normal: X = op(A) (M x K), Y = op(B) (K x N).  Swapped (skinny M): X = op(B)^T
+  // (N x K), Y = op(A)^T (K x M), output transposed.  "mn-major" = the non-K index is the contiguous one.
+  struct Opnd { const void* p; int64_t mn, ld, st; bool mn_major; };
+  Opnd X = {c.A, c.m, c.lda, c.sa, !c.ta}, Y = {c.B, c.n, c.ldb, c.sb, c.tb};
+  if (plan.swap) { Opnd t = X; X = Y; Y = t; }
+  const bool a_mn = X.mn_major, b_mn = Y.mn_major;
   CUtensorMap tmA, tmB;
-  if (!make_operand_map(&tmA, es, dt, c.A, c.m, c.k, c.lda, c.batch, c.sa, !a_mn, BM) ||
-      !make_operand_map(&tmB, es, dt, c.B, c.n, c.k, c.ldb, c.batch, c.sb, !b_mn, bn / cg)) {
+  if (!make_operand_map(&tmA, es, dt, X.p, X.mn, c.k, X.ld, c.batch, X.st, !a_mn, BM) ||
+      !make_operand_map(&tmB, es, dt, Y.p, Y.mn, c.k, Y.ld, c.batch, Y.st, !b_mn, bn / cg)) {
     h->last_error = "cuTensorMapEncodeTiled failed";
     return PBX_ERR_CUDA;
   }
   TcParams p;
   p.C = c.C; p.ws = (float*)h->ws;
-  p.M = c.m; p.N = c.n; p.K = c.k; p.ldc = c.ldc; p.sc = c.sc;
+  p.M = X.mn; p.N = Y.mn; p.K = c.k; p.ldc = c.ldc; p.sc = c.sc;
   p.alpha = (float)c.alpha; p.beta = (float)c.beta;
   p.batch = (int)c.batch; p.slices = slices;
-  p.m_tiles = (int)((c.m + BM * cg - 1) / (BM * cg));
-  p.n_tiles = (int)((c.n + bn - 1) / bn);
+  p.m_tiles = (int)((p.M + BM * cg - 1) / (BM * cg));
+  p.n_tiles = (int)((p.N + bn - 1) / bn);
   p.group_m = cg == 2 ? 8 : 16;
   p.kb_total = (int)((c.k + bk - 1) / bk);
   p.kb_per_slice = (p.kb_total + slices - 1) / slices;
@@ -682,8 +755,10 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
   // default: raw fp32 tile as the hi operand (verified on B200: kind::tf32 ignores the low 13 mantissa bits)
   const int raw_hi_env = getenv("PBX_TF32_RAW_HI") ? atoi(getenv("PBX_TF32_RAW_HI")) : 1;
   p.raw_hi = raw_hi_env;
-  p.a_batched = (c.batch > 1 && c.sa > 0) ? 1 : 0;
-  p.b_batched = (c.batch > 1 && c.sb > 0) ? 1 : 0;
+  p.a_batched = (c.batch > 1 && X.st > 0) ? 1 : 0;
+  p.b_batched = (c.batch > 1 && Y.st > 0) ? 1 : 0;
+  const int64_t eo = (int64_t)pbx_out_size(c.dtype);
+  p.c_vec = (((uintptr_t)c.C % 16 == 0) && (c.ldc * eo) % 16 == 0 && (c.sc * eo) % 16 == 0) ? 1 : 0;
   p.total_tiles = (int64_t)p.m_tiles * p.n_tiles * c.batch * slices;
 
   // 16-bit C with beta == 0 leaves through shared memory + TMA stores when C is TMA-legal

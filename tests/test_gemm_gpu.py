@@ -219,6 +219,21 @@ def test_split_k_mid_k_few_tiles(handle):
         assert r.kernel == "tcgen05" and r.split_k > 1, (dt, m, n, k, r)
 
 
+@pytest.mark.parametrize("dt", ["f32", "f16", "bf16", "f16f32", "bf16f32"])
+def test_skinny_m_swapped_operands(handle, dt):
+    """M <= 64 < N runs as C^T = op(B)^T op(A)^T with a transposed-store epilogue (vector stores, TMA store for
+    16-bit C, split-K partials); it must agree with the un-swapped plan (PBX_TC_SWAP=0) on ragged shapes."""
+    cases = []
+    for env in ((), (("PBX_TC_SWAP", "0"),)):
+        for m, n, k, be, (ta, tb) in itertools.product([8, 40, 64], [136, 1000], [72, 520], [0.0, 0.5], TRANS):
+            cases.append(Case(dtype=dt, transa=ta, transb=tb, m=m, n=n, k=k, alpha=1.5, beta=be, kernel=TCGEN05, env=env))
+        cases.append(Case(dtype=dt, m=24, n=264, k=4104, alpha=1.0, beta=0.5, kernel=TCGEN05, split_k=5, env=env))
+        cases.append(Case(dtype=dt, m=56, n=200, k=136, alpha=1.0, beta=0.0, ldc_mul=3, kernel=TCGEN05, env=env))
+        cases.append(Case(dtype=dt, api="strided", transa="t", m=64, n=392, k=72, alpha=1.0, beta=0.0, batch=6,
+                          stride_a_mul=0, kernel=TCGEN05, env=env))
+    _run_all(handle, cases)
+
+
 def test_unaligned_operands_repacked_to_tensor_cores(handle):
     """Odd leading dimensions / element offsets (the reference's OffsetNonZero and LD-multiplied grids, and e.g.
     64x147x423200 of its ResNet sweep) cannot be addressed by TMA: the operand is re-laid out once and the call
