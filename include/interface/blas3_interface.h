@@ -8,10 +8,16 @@
 // The remaining front-end rules (alpha==0 shortcut, trans / stride validation, beta==0
 // specialisation) live behind the C-ABI so every binding shares them; invalid arguments come
 // back as status codes and are rethrown here as the reference's std::invalid_argument texts.
+//
+// Also here, built on the same path: blas::_symm (:137-147 ->
+// src/interface/symm_interface.hpp:35-75), blas::_trsm (:125-135 -> src/interface/trsm_interface.hpp:105-387) and
+// the complex instantiations of _gemm* (BLAS_ENABLE_COMPLEX; element type std::complex<T>, which is layout
+// compatible with the reference's sycl::ext::oneapi::experimental::complex<T>).
 #pragma once
 #include <cuda_bf16.h>
 
 #include <cctype>
+#include <complex>
 #include <iostream>
 #include <stdexcept>
 #include <type_traits>
@@ -32,10 +38,15 @@ template <> struct pbx_dtype_of<sycl::half, float> { static constexpr int value 
 template <> struct pbx_dtype_of<__nv_bfloat16, __nv_bfloat16> { static constexpr int value = PBX_BF16; };
 template <> struct pbx_dtype_of<__nv_bfloat16, float> { static constexpr int value = PBX_BF16_F32; };
 
+template <typename T> struct is_std_complex : std::false_type {};
+template <typename T> struct is_std_complex<std::complex<T>> : std::true_type {};
+
 inline void throw_on_status(pbx_handle_t h, int st) {
   if (st == PBX_OK) return;
-  if (st >= PBX_ERR_INVALID_TRANSA && st <= PBX_ERR_INVALID_STRIDEB)
-    throw std::invalid_argument(pbx_status_string(st));  // gemm_interface.hpp:144-165
+  if ((st >= PBX_ERR_INVALID_TRANSA && st <= PBX_ERR_INVALID_STRIDEB) ||
+      (st >= PBX_ERR_INVALID_UPLO && st <= PBX_ERR_TRSM_DIAG))
+    // gemm_interface.hpp:144-165, symm_interface.hpp:51-72, trsm_interface.hpp:112-128
+    throw std::invalid_argument(pbx_status_string(st));
   std::string msg = std::string(pbx_status_string(st)) + ": " + pbx_last_error(h);
   std::cerr << "[portblas-b200] " << msg << std::endl;  // reference prints sycl::exception text (kernel_constructor.hpp:213-216)
   throw std::runtime_error(msg);
@@ -53,6 +64,30 @@ typename sb_handle_t::event_t _gemm_backend(sb_handle_t& sb_handle, char _TransA
   using in1_t = typename ValueType<container_1_t>::type;
   using out_t = typename ValueType<container_2_t>::type;
   static_assert(std::is_same_v<in_t, in1_t>, "A and B must share an element type");
+  if constexpr (is_std_complex<out_t>::value) {
+    // complex GEMM: strided batches only, as the reference (backend/default.hpp:202-246)
+    using real_t = typename out_t::value_type;
+    static_assert(std::is_same_v<in_t, out_t>, "complex GEMM: A, B and C share one element type");
+    if (batch_type != gemm_batch_type_t::strided && batch_size > index_t(1))
+      throw unsupported_exception("complex GEMM supports strided batches only");
+    const real_t alpha[2] = {static_cast<real_t>(_alpha.real()), static_cast<real_t>(_alpha.imag())};
+    const real_t beta[2] = {static_cast<real_t>(_beta.real()), static_cast<real_t>(_beta.imag())};
+    auto q = sb_handle.get_queue();
+    sycl::event ev = q.submit([&](sycl::handler& cgh) {
+      cgh.depends_on(_dependencies);
+      int st;
+      if constexpr (std::is_same_v<real_t, double>)
+        st = pbx_zgemm(cgh.pbx(), _TransA, _TransB, _M, _N, _K, alpha, get_device_ptr(a_), _lda, _stridea,
+                       get_device_ptr(b_), _ldb, _strideb, beta, const_cast<out_t*>(get_device_ptr(_C)), _ldc,
+                       _stridec, batch_size);
+      else
+        st = pbx_cgemm(cgh.pbx(), _TransA, _TransB, _M, _N, _K, alpha, get_device_ptr(a_), _lda, _stridea,
+                       get_device_ptr(b_), _ldb, _strideb, beta, const_cast<out_t*>(get_device_ptr(_C)), _ldc,
+                       _stridec, batch_size);
+      throw_on_status(cgh.pbx(), st);
+    });
+    return typename sb_handle_t::event_t{ev};
+  } else {
   constexpr int dtype = pbx_dtype_of<in_t, out_t>::value;
   // scalars cross the C-ABI as double (fp64) or float (everything else)
   using scalar_abi_t = std::conditional_t<std::is_same_v<out_t, double>, double, float>;
@@ -68,6 +103,54 @@ typename sb_handle_t::event_t _gemm_backend(sb_handle_t& sb_handle, char _TransA
                             const_cast<std::remove_const_t<out_t>*>(get_device_ptr(_C)), static_cast<int64_t>(_ldc),
                             static_cast<int64_t>(_stridec), static_cast<int64_t>(batch_size),
                             static_cast<int>(batch_type));
+    throw_on_status(cgh.pbx(), st);
+  });
+  return typename sb_handle_t::event_t{ev};
+  }
+}
+
+// C <- alpha*A*B + beta*C (side 'l') or alpha*B*A + beta*C (side 'r'), A symmetric (symm_interface.hpp:35-75)
+template <typename sb_handle_t, typename container_0_t, typename container_1_t, typename container_2_t,
+          typename element_t, typename index_t>
+typename sb_handle_t::event_t _symm(sb_handle_t& sb_handle, char _side, char _uplo, index_t _M, index_t _N,
+                                    element_t _alpha, container_0_t a_, index_t _lda, container_1_t b_, index_t _ldb,
+                                    element_t _beta, container_2_t _C, index_t _ldc,
+                                    const typename sb_handle_t::event_t& _dependencies) {
+  using in_t = typename ValueType<container_0_t>::type;
+  using out_t = typename ValueType<container_2_t>::type;
+  constexpr int dtype = pbx_dtype_of<in_t, out_t>::value;
+  using scalar_abi_t = std::conditional_t<std::is_same_v<out_t, double>, double, float>;
+  const scalar_abi_t alpha = static_cast<scalar_abi_t>(_alpha), beta = static_cast<scalar_abi_t>(_beta);
+  auto q = sb_handle.get_queue();
+  sycl::event ev = q.submit([&](sycl::handler& cgh) {
+    cgh.depends_on(_dependencies);
+    const int st = pbx_symm(cgh.pbx(), dtype, _side, _uplo, static_cast<int64_t>(_M), static_cast<int64_t>(_N), &alpha,
+                            get_device_ptr(a_), static_cast<int64_t>(_lda), get_device_ptr(b_),
+                            static_cast<int64_t>(_ldb), &beta,
+                            const_cast<std::remove_const_t<out_t>*>(get_device_ptr(_C)), static_cast<int64_t>(_ldc));
+    throw_on_status(cgh.pbx(), st);
+  });
+  return typename sb_handle_t::event_t{ev};
+}
+
+// op(A)*X = alpha*B or X*op(A) = alpha*B, X overwrites B (trsm_interface.hpp:105-387)
+template <typename sb_handle_t, typename container_0_t, typename container_1_t, typename element_t,
+          typename index_t>
+typename sb_handle_t::event_t _trsm(sb_handle_t& sb_handle, char side, char uplo, char trans, char diag, index_t M,
+                                    index_t N, element_t alpha_, container_0_t A, index_t lda, container_1_t B,
+                                    index_t ldb, const typename sb_handle_t::event_t& _dependencies) {
+  using in_t = typename ValueType<container_0_t>::type;
+  using out_t = typename ValueType<container_1_t>::type;
+  constexpr int dtype = pbx_dtype_of<in_t, out_t>::value;
+  static_assert(dtype == PBX_F32 || dtype == PBX_F64, "_trsm: float or double");
+  using scalar_abi_t = std::conditional_t<std::is_same_v<out_t, double>, double, float>;
+  const scalar_abi_t alpha = static_cast<scalar_abi_t>(alpha_);
+  auto q = sb_handle.get_queue();
+  sycl::event ev = q.submit([&](sycl::handler& cgh) {
+    cgh.depends_on(_dependencies);
+    const int st = pbx_trsm(cgh.pbx(), dtype, side, uplo, trans, diag, static_cast<int64_t>(M),
+                            static_cast<int64_t>(N), &alpha, get_device_ptr(A), static_cast<int64_t>(lda),
+                            const_cast<std::remove_const_t<out_t>*>(get_device_ptr(B)), static_cast<int64_t>(ldb));
     throw_on_status(cgh.pbx(), st);
   });
   return typename sb_handle_t::event_t{ev};
@@ -146,6 +229,24 @@ typename sb_handle_t::event_t _gemm_strided_batched(sb_handle_t& sb_handle, char
                                                     const typename sb_handle_t::event_t& _dependencies = {}) {
   return internal::_gemm_strided_batched(sb_handle, _TransA, _TransB, _M, _N, _K, _alpha, a_, _lda, _stridea, b_,
                                          _ldb, _strideb, _beta, _C, _ldc, _stridec, batch_size, _dependencies);
+}
+
+template <typename sb_handle_t, typename container_0_t, typename container_1_t, typename element_t,
+          typename index_t>
+typename sb_handle_t::event_t inline _trsm(sb_handle_t& sb_handle, char side, char uplo, char trans, char diag,
+                                           index_t M, index_t N, element_t alpha, container_0_t A, index_t lda,
+                                           container_1_t B, index_t ldb,
+                                           const typename sb_handle_t::event_t& _dependencies = {}) {
+  return internal::_trsm(sb_handle, side, uplo, trans, diag, M, N, alpha, A, lda, B, ldb, _dependencies);
+}
+
+template <typename sb_handle_t, typename container_0_t, typename container_1_t, typename container_2_t,
+          typename element_t, typename index_t>
+typename sb_handle_t::event_t _symm(sb_handle_t& sb_handle, char _side, char _uplo, index_t _M, index_t _N,
+                                    element_t _alpha, container_0_t a_, index_t _lda, container_1_t b_, index_t _ldb,
+                                    element_t _beta, container_2_t _C, index_t _ldc,
+                                    const typename sb_handle_t::event_t& _dependencies = {}) {
+  return internal::_symm(sb_handle, _side, _uplo, _M, _N, _alpha, a_, _lda, b_, _ldb, _beta, _C, _ldc, _dependencies);
 }
 
 }  // namespace blas

@@ -52,7 +52,14 @@ typedef enum pbx_status {
   PBX_ERR_INVALID_ARG = 6,     /* null handle, unknown dtype/batch_type, negative dims */
   PBX_ERR_CUDA = 7,            /* a CUDA runtime / driver call failed; see pbx_last_error() */
   PBX_ERR_NO_DEVICE = 8,       /* no sm_100 device: this library has no fallback */
-  PBX_ERR_WORKSPACE = 9        /* split-K workspace could not be allocated */
+  PBX_ERR_WORKSPACE = 9,       /* a pooled temporary (split-K workspace, packed operand) could not be allocated */
+  PBX_ERR_INVALID_UPLO = 10,   /* _symm: "invalid _uplo"  src/interface/symm_interface.hpp:51-53 */
+  PBX_ERR_INVALID_SIDE = 11,   /* _symm: "invalid _side"  src/interface/symm_interface.hpp:70-72 */
+  PBX_ERR_TRSM_SIZE = 12,      /* _trsm: "invalid matrix size argument"  src/interface/trsm_interface.hpp:112-114 */
+  PBX_ERR_TRSM_SIDE = 13,      /* _trsm: "invalid Side argument"       trsm_interface.hpp:121-122 */
+  PBX_ERR_TRSM_UPLO = 14,      /* _trsm: "invalid Triangle argument"   trsm_interface.hpp:123-124 */
+  PBX_ERR_TRSM_TRANS = 15,     /* _trsm: "invalid Transpose argument"  trsm_interface.hpp:125-126 */
+  PBX_ERR_TRSM_DIAG = 16       /* _trsm: "invalid Diagonal argument"   trsm_interface.hpp:127-128 */
 } pbx_status_t;
 
 /* ---- element types (in -> out) ----------------------------------------- *
@@ -157,6 +164,43 @@ int pbx_bf16gemm(pbx_handle_t h, char transa, char transb, int64_t m, int64_t n,
  * beta == 1: no launch.  beta == 0: stores zeros without reading C.          */
 int pbx_scal_matrix(pbx_handle_t h, int dtype, int64_t m, int64_t n, const void* beta,
                     void* C, int64_t ldc, int64_t stridec, int64_t batch);
+
+/* ---- routines built on the GEMM path -------------------------------
+ *
+ * pbx_symm:  C <- alpha*A*B + beta*C (side 'l', A is MxM) or alpha*B*A + beta*C (side 'r', A is NxN),
+ *   A symmetric with only its `uplo` triangle referenced.  Replaces blas::internal::_symm
+ *   (src/interface/symm_interface.hpp:35-75), which runs the GEMM kernels with a mirroring operand
+ *   loader (gemm_local.hpp:813-873).  Here one HBM-bound pass mirrors the triangle into a pooled full
+ *   matrix, then the ordinary tensor-core GEMM runs.  dtype: PBX_F32, PBX_F64, PBX_F16 or PBX_BF16.
+ *   Checks, in the reference's order: uplo, side; then the GEMM front end (alpha == 0 shortcut ...).    */
+int pbx_symm(pbx_handle_t h, int dtype, char side, char uplo, int64_t m, int64_t n, const void* alpha,
+             const void* A, int64_t lda, const void* B, int64_t ldb, const void* beta, void* C, int64_t ldc);
+
+/* pbx_trsm:  solves op(A)*X = alpha*B (side 'l') or X*op(A) = alpha*B (side 'r') in place of B (MxN);
+ *   A triangular (`uplo`), `diag` 'u' = unit diagonal assumed, trans 'n' / 't' only (the reference rejects
+ *   'c', trsm_interface.hpp:125).  Replaces blas::internal::_trsm (src/interface/trsm_interface.hpp:105-387):
+ *   the same inverse-of-diagonal-blocks + GEMM scheme (DiagonalBlocksInverter, src/operations/blas3/trsm.hpp),
+ *   but with 64/128-wide diagonal blocks and a recursive split so that the trailing updates are large
+ *   tensor-core GEMMs instead of rank-16 ones.  The other triangle of A is never read (it may hold NaN).
+ *   dtype: PBX_F32 or PBX_F64.                                                                           */
+int pbx_trsm(pbx_handle_t h, int dtype, char side, char uplo, char trans, char diag, int64_t m, int64_t n,
+             const void* alpha, const void* A, int64_t lda, void* B, int64_t ldb);
+
+/* pbx_cgemm / pbx_zgemm:  complex GEMM (BLAS_ENABLE_COMPLEX builds of the reference: gemm.cpp.in,
+ *   backend/default.hpp:202-246, nvidia_gpu.hpp:237-260), interleaved (re, im) storage, strided batches only
+ *   (the reference hard-codes gemm_batch_type_t::strided for complex).  alpha / beta point to host
+ *   {re, im} pairs.  Computed as ONE real GEMM of twice the size on the tensor-core path:
+ *   [Cr; Ci] = [Ar -Ai; Ai Ar] * [Br; Bi], framed by an HBM-bound planar split and a combine pass that
+ *   applies alpha and beta.  Same front-end rules as pbx_gemm.  'c' is treated like 't' (NO conjugation),
+ *   exactly as the reference does (gemm_interface.hpp:150-151: _TrA = _TransA != 'n');
+ *   pbx_set_conj_transpose(h, 1) switches to BLAS-standard conjugate transposes.                          */
+int pbx_cgemm(pbx_handle_t h, char transa, char transb, int64_t m, int64_t n, int64_t k, const float* alpha,
+              const void* A, int64_t lda, int64_t stridea, const void* B, int64_t ldb, int64_t strideb,
+              const float* beta, void* C, int64_t ldc, int64_t stridec, int64_t batch);
+int pbx_zgemm(pbx_handle_t h, char transa, char transb, int64_t m, int64_t n, int64_t k, const double* alpha,
+              const void* A, int64_t lda, int64_t stridea, const void* B, int64_t ldb, int64_t strideb,
+              const double* beta, void* C, int64_t ldc, int64_t stridec, int64_t batch);
+int pbx_set_conj_transpose(pbx_handle_t h, int enable);
 
 /* ---- host-buffer convenience path (used for the end-to-end metric) -------
  * Same semantics as pbx_gemm, but A, B, C are HOST pointers (ideally pinned):

@@ -46,6 +46,15 @@ SYMBOLS = {
     "pbx_hsgemm": (c_int, [c_void_p, c_char, c_char] + _GEMM_TAIL),
     "pbx_bf16gemm": (c_int, [c_void_p, c_char, c_char] + _GEMM_TAIL),
     "pbx_scal_matrix": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64]),
+    "pbx_symm": (c_int, [c_void_p, c_int, c_char, c_char, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                         c_void_p, c_void_p, c_int64]),
+    "pbx_trsm": (c_int, [c_void_p, c_int, c_char, c_char, c_char, c_char, c_int64, c_int64, c_void_p, c_void_p, c_int64,
+                         c_void_p, c_int64]),
+    "pbx_cgemm": (c_int, [c_void_p, c_char, c_char, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64,
+                          c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64]),
+    "pbx_zgemm": (c_int, [c_void_p, c_char, c_char, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64,
+                          c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64]),
+    "pbx_set_conj_transpose": (c_int, [c_void_p, c_int]),
     "pbx_gemm_host": (c_int, [c_void_p, c_int, c_char, c_char] + _GEMM_TAIL),
     "pbx_malloc": (c_int, [c_void_p, POINTER(c_void_p), c_int64]),
     "pbx_free": (c_int, [c_void_p, c_void_p]),

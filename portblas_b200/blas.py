@@ -7,6 +7,9 @@ Names, argument order, argument meaning and error behaviour follow the reference
   blas::_gemm                        include/interface/blas3_interface.h:88-95
   blas::_gemm_batched                include/interface/blas3_interface.h:99-109
   blas::_gemm_strided_batched        include/interface/blas3_interface.h:113-123
+  blas::_trsm                        include/interface/blas3_interface.h:125-135
+  blas::_symm                        include/interface/blas3_interface.h:137-147
+  complex _gemm* (BLAS_ENABLE_COMPLEX): torch.complex64 / complex128 containers, complex alpha / beta
 
 so that tests/ read like test/unittest/blas3/*gemm*.  (The C++ mirror of the same interface lives
 in include/portblas.hpp; both funnel into the same extern "C" entry points.)
@@ -41,8 +44,10 @@ def _check(h: "SB_Handle", status: int) -> None:
         return
     lib = _lib.load()
     text = lib.pbx_status_string(status).decode()
-    if 1 <= status <= 5:
-        raise ValueError(text)  # reference: std::invalid_argument(text), gemm_interface.hpp:144-165
+    if 1 <= status <= 5 or 10 <= status <= 16:
+        # reference: std::invalid_argument(text), gemm_interface.hpp:144-165, symm_interface.hpp:51-72,
+        # trsm_interface.hpp:112-128
+        raise ValueError(text)
     detail = lib.pbx_last_error(h._h).decode() if h is not None and h._h else ""
     raise PbxError(f"{text}: {detail}" if detail else text)
 
@@ -94,6 +99,10 @@ class SB_Handle:
     def set_split_k(self, slices: int) -> None:
         _check(self, self._lib.pbx_set_split_k(self._h, int(slices)))
 
+    def set_conj_transpose(self, enable: bool) -> None:
+        """complex GEMM: False (default) = 'c' behaves like 't', as in the reference; True = BLAS conjugate."""
+        _check(self, self._lib.pbx_set_conj_transpose(self._h, int(bool(enable))))
+
     @property
     def last_kernel(self) -> str:
         return _lib.KERNEL_NAMES[self._lib.pbx_last_kernel(self._h)]
@@ -139,6 +148,11 @@ def _gemm_backend(sb_handle: SB_Handle, transa: str, transb: str, m: int, n: int
     for t in (a, b, c):
         if not (isinstance(t, torch.Tensor) and t.is_cuda and t.is_contiguous()):
             raise TypeError("containers must be contiguous CUDA tensors (device USM analogue)")
+    if c.dtype in (torch.complex64, torch.complex128):
+        if batch_type != gemm_batch_type_t.strided and batch_size > 1:
+            raise TypeError("complex GEMM supports strided batches only (as the reference)")
+        return _gemm_complex(sb_handle, transa, transb, m, n, k, alpha, a, lda, stridea, b, ldb, strideb, beta, c,
+                             ldc, stridec, batch_size)
     dt = _dtype_of(a, b, c)
     al, be = _scalar(dt, float(alpha)), _scalar(dt, float(beta))
     st = sb_handle._lib.pbx_gemm(
@@ -147,6 +161,53 @@ def _gemm_backend(sb_handle: SB_Handle, transa: str, transb: str, m: int, n: int
         ctypes.c_void_p(b.data_ptr()), int(ldb), int(strideb),
         ctypes.cast(ctypes.pointer(be), ctypes.c_void_p), ctypes.c_void_p(c.data_ptr()), int(ldc), int(stridec),
         int(batch_size), int(batch_type))
+    _check(sb_handle, st)
+
+
+def _gemm_complex(sb_handle, transa, transb, m, n, k, alpha, a, lda, stridea, b, ldb, strideb, beta, c, ldc, stridec,
+                  batch_size) -> None:
+    if not (a.dtype == b.dtype == c.dtype):
+        raise TypeError("complex GEMM: A, B and C must share one element type")
+    z = c.dtype == torch.complex128
+    ct = ctypes.c_double if z else ctypes.c_float
+    al, be = complex(alpha), complex(beta)
+    al_a, be_a = (ct * 2)(al.real, al.imag), (ct * 2)(be.real, be.imag)
+    fn = sb_handle._lib.pbx_zgemm if z else sb_handle._lib.pbx_cgemm
+    st = fn(sb_handle._h, str(transa).encode()[:1], str(transb).encode()[:1], int(m), int(n), int(k),
+            ctypes.cast(al_a, ctypes.c_void_p), ctypes.c_void_p(a.data_ptr()), int(lda), int(stridea),
+            ctypes.c_void_p(b.data_ptr()), int(ldb), int(strideb), ctypes.cast(be_a, ctypes.c_void_p),
+            ctypes.c_void_p(c.data_ptr()), int(ldc), int(stridec), int(batch_size))
+    _check(sb_handle, st)
+
+
+def _symm(sb_handle, _side, _uplo, _M, _N, _alpha, a_, _lda, b_, _ldb, _beta, _C, _ldc) -> None:
+    """C <- alpha*A*B + beta*C (side 'l') or alpha*B*A + beta*C (side 'r'), A symmetric
+    (blas3_interface.h:137-147 -> symm_interface.hpp:35-75)."""
+    for t in (a_, b_, _C):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.is_contiguous()):
+            raise TypeError("containers must be contiguous CUDA tensors (device USM analogue)")
+    dt = _dtype_of(a_, b_, _C)
+    al, be = _scalar(dt, float(_alpha)), _scalar(dt, float(_beta))
+    st = sb_handle._lib.pbx_symm(
+        sb_handle._h, dt, str(_side).encode()[:1], str(_uplo).encode()[:1], int(_M), int(_N),
+        ctypes.cast(ctypes.pointer(al), ctypes.c_void_p), ctypes.c_void_p(a_.data_ptr()), int(_lda),
+        ctypes.c_void_p(b_.data_ptr()), int(_ldb), ctypes.cast(ctypes.pointer(be), ctypes.c_void_p),
+        ctypes.c_void_p(_C.data_ptr()), int(_ldc))
+    _check(sb_handle, st)
+
+
+def _trsm(sb_handle, side, uplo, trans, diag, M, N, alpha, A, lda, B, ldb) -> None:
+    """op(A)*X = alpha*B or X*op(A) = alpha*B, X overwrites B (blas3_interface.h:125-135 ->
+    trsm_interface.hpp:105-387)."""
+    for t in (A, B):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.is_contiguous()):
+            raise TypeError("containers must be contiguous CUDA tensors (device USM analogue)")
+    dt = _dtype_of(A, B, B)
+    al = _scalar(dt, float(alpha))
+    st = sb_handle._lib.pbx_trsm(
+        sb_handle._h, dt, str(side).encode()[:1], str(uplo).encode()[:1], str(trans).encode()[:1],
+        str(diag).encode()[:1], int(M), int(N), ctypes.cast(ctypes.pointer(al), ctypes.c_void_p),
+        ctypes.c_void_p(A.data_ptr()), int(lda), ctypes.c_void_p(B.data_ptr()), int(ldb))
     _check(sb_handle, st)
 
 

@@ -18,7 +18,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OUT = HERE / "libpbx_gemm.so"
 OBJ_DIR = HERE / "csrc" / "_obj"
-SOURCES = ["pbx_api.cu", "pbx_host.cu", "gemm_simt.cu", "gemm_dmma.cu", "gemm_tcgen05.cu"]
+SOURCES = ["pbx_api.cu", "pbx_host.cu", "gemm_simt.cu", "gemm_dmma.cu", "gemm_tcgen05.cu", "blas3_ext.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

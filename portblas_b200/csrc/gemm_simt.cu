@@ -342,6 +342,9 @@ int pbx_launch_repack(pbx_handle_t h, int elem_bytes, const void* src, void* dst
   else if (elem_bytes == 4)
     repack_kernel<uint32_t><<<(unsigned)blocks, 256, 0, h->stream>>>((const uint32_t*)src, (uint32_t*)dst, rows, cols,
                                                                   ld_src, ld_dst, stride_src, stride_dst, batch, chunks);
+  else if (elem_bytes == 8)
+    repack_kernel<uint64_t><<<(unsigned)blocks, 256, 0, h->stream>>>((const uint64_t*)src, (uint64_t*)dst, rows, cols,
+                                                                  ld_src, ld_dst, stride_src, stride_dst, batch, chunks);
   else
     return PBX_ERR_INVALID_ARG;
   h->launches++;

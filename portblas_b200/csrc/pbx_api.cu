@@ -25,6 +25,13 @@ const char* pbx_status_string(int status) {
     case PBX_ERR_CUDA: return "CUDA error";
     case PBX_ERR_NO_DEVICE: return "no sm_100 CUDA device (this library has no CPU fallback)";
     case PBX_ERR_WORKSPACE: return "workspace allocation failed";
+    case PBX_ERR_INVALID_UPLO: return "invalid _uplo";
+    case PBX_ERR_INVALID_SIDE: return "invalid _side";
+    case PBX_ERR_TRSM_SIZE: return "invalid matrix size argument";
+    case PBX_ERR_TRSM_SIDE: return "invalid Side argument";
+    case PBX_ERR_TRSM_UPLO: return "invalid Triangle argument";
+    case PBX_ERR_TRSM_TRANS: return "invalid Transpose argument";
+    case PBX_ERR_TRSM_DIAG: return "invalid Diagonal argument";
   }
   return "unknown status";
 }
@@ -67,6 +74,8 @@ int pbx_destroy(pbx_handle_t h) {
     if (h->stage[i]) cudaFree(h->stage[i]);
   for (int i = 0; i < 2; ++i)
     if (h->pack[i]) cudaFree(h->pack[i]);
+  for (int i = 0; i < 4; ++i)
+    if (h->aux[i]) cudaFree(h->aux[i]);
   for (cudaEvent_t e : h->events) cudaEventDestroy(e);
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_out) cudaStreamDestroy(h->s_out);
@@ -111,6 +120,26 @@ int pbx_ensure_workspace(pbx_handle_t h, int64_t bytes) {
     return PBX_ERR_WORKSPACE;
   }
   h->ws_bytes = rounded;
+  return PBX_OK;
+}
+
+int pbx_ensure_aux(pbx_handle_t h, int i, int64_t bytes) {
+  if (i < 0 || i >= 4) return PBX_ERR_INVALID_ARG;
+  if (bytes <= h->aux_bytes[i]) return PBX_OK;
+  if (h->aux[i]) {
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaFree(h->aux[i]) != cudaSuccess) {
+      h->last_error = "temporary free failed";
+      return PBX_ERR_WORKSPACE;
+    }
+    h->aux[i] = nullptr; h->aux_bytes[i] = 0;
+  }
+  const int64_t rounded = ((bytes + (1 << 20) - 1) >> 20) << 20;
+  if (cudaMalloc(&h->aux[i], (size_t)rounded) != cudaSuccess) {
+    cudaGetLastError();
+    h->last_error = "temporary allocation failed";
+    return PBX_ERR_WORKSPACE;
+  }
+  h->aux_bytes[i] = rounded;
   return PBX_OK;
 }
 

@@ -46,6 +46,11 @@ struct pbx_handle_s {
   // aligned copies of TMA-illegal operands (pbx_api.cu: repack_for_tma); grow monotonically
   void* pack[2] = {nullptr, nullptr};
   int64_t pack_bytes[2] = {0, 0};
+  // pooled temporaries of the GEMM-built routines (blas3_ext.cu: symmetrised A, planar complex operands,
+  // inverted diagonal blocks / X of trsm); grow monotonically, stream ordered
+  void* aux[4] = {nullptr, nullptr, nullptr, nullptr};
+  int64_t aux_bytes[4] = {0, 0, 0, 0};
+  int conj_transpose = 0;   // complex GEMM: 0 = 'c' behaves as 't' (the reference), 1 = BLAS conjugate-transpose
   // staging buffers for pbx_gemm_host
   void* stage[3] = {nullptr, nullptr, nullptr};
   int64_t stage_bytes[3] = {0, 0, 0};
@@ -81,6 +86,7 @@ static inline size_t pbx_out_size(int dtype) {
 }
 
 int pbx_ensure_workspace(pbx_handle_t h, int64_t bytes);
+int pbx_ensure_aux(pbx_handle_t h, int i, int64_t bytes);
 
 // ---- kernel families (each returns a pbx_status_t) -----------------------
 // slices > 1: the kernel writes raw fp32/fp64 partial sums to h->ws laid out

@@ -7,6 +7,7 @@
 #include <sycl/sycl.hpp>
 
 #include <cmath>
+#include <complex>
 #include <cstdio>
 #include <random>
 #include <vector>
@@ -118,6 +119,100 @@ bool run_batched(blas::SB_Handle& sb) {
   return ok;
 }
 
+// _symm, _trsm and complex _gemm: the routines built on the GEMM path
+bool run_symm_trsm_complex(blas::SB_Handle& sb) {
+  using namespace blas;
+  auto q = sb.get_queue();
+  bool ok = true;
+  {  // _symm left / upper: only the upper triangle of A is referenced
+    const int m = 200, n = 130, lda = m + 1, ldb = m, ldc = m + 3;
+    std::vector<float> a((size_t)lda * m), b((size_t)ldb * n), c((size_t)ldc * n), want;
+    fill(a, 11); fill(b, 12); fill(c, 13);
+    std::vector<float> full(a);
+    for (int j = 0; j < m; ++j)
+      for (int i = j + 1; i < m; ++i) { full[i + (size_t)j * lda] = a[j + (size_t)i * lda]; a[i + (size_t)j * lda] = NAN; }
+    want = c;
+    host_gemm('n', 'n', m, n, m, 1.5, full, lda, b, ldb, 0.5, want, ldc);
+    auto a_d = make_sycl_iterator_buffer<float>(a.data(), a.size());
+    auto b_d = make_sycl_iterator_buffer<float>(b.data(), b.size());
+    float* c_u = sycl::malloc_device<float>(c.size(), q);
+    helper::copy_to_device(q, c.data(), c_u, c.size());
+    sb.wait(_symm(sb, 'l', 'u', m, n, 1.5f, a_d, lda, b_d, ldb, 0.5f, c_u, ldc));
+    std::vector<float> got(c.size());
+    sb.wait(helper::copy_to_host(q, c_u, got.data(), got.size()));
+    sycl::free(c_u, q);
+    ok &= close(got, want, 2e-5, "_symm float left/upper 200x130");
+  }
+  {  // _trsm left / lower / no-trans / non-unit: check the residual A*X = alpha*B
+    const int m = 300, n = 70, lda = m, ldb = m + 2;
+    std::vector<double> a((size_t)lda * m, NAN), b((size_t)ldb * n), x;
+    std::mt19937 gen(21);
+    std::uniform_real_distribution<double> dis(-1.0, 1.0);
+    for (int j = 0; j < m; ++j)
+      for (int i = j; i < m; ++i) a[i + (size_t)j * lda] = (i == j) ? 4.0 + dis(gen) : dis(gen) / m;
+    fill(b, 22);
+    double* a_u = sycl::malloc_device<double>(a.size(), q);
+    double* b_u = sycl::malloc_device<double>(b.size(), q);
+    helper::copy_to_device(q, a.data(), a_u, a.size());
+    helper::copy_to_device(q, b.data(), b_u, b.size());
+    sb.wait(_trsm(sb, 'l', 'l', 'n', 'n', m, n, 2.0, a_u, lda, b_u, ldb));
+    x.resize(b.size());
+    sb.wait(helper::copy_to_host(q, b_u, x.data(), x.size()));
+    sycl::free(a_u, q); sycl::free(b_u, q);
+    double worst = 0;
+    for (int j = 0; j < n; ++j)
+      for (int i = 0; i < m; ++i) {
+        double acc = 0;
+        for (int l = 0; l <= i; ++l) acc += a[i + (size_t)l * lda] * x[l + (size_t)j * ldb];
+        worst = std::max(worst, std::fabs(acc - 2.0 * b[i + (size_t)j * ldb]) / (std::fabs(2.0 * b[i + (size_t)j * ldb]) + 1.0));
+      }
+    const bool pass = worst < 1e-12 && x[m] == b[m];   // padding row untouched
+    std::printf("%-46s max residual %.3e  %s\n", "_trsm double left/lower 300x70", worst, pass ? "PASS" : "FAIL");
+    ok &= pass;
+  }
+  {  // complex _gemm (BLAS_ENABLE_COMPLEX): C = alpha*A^T*B + beta*C
+    using cf = std::complex<float>;
+    const int m = 65, n = 40, k = 100, lda = k, ldb = k + 1, ldc = m;
+    std::vector<cf> a((size_t)lda * m), b((size_t)ldb * n), c((size_t)ldc * n), want;
+    std::mt19937 gen(31);
+    std::uniform_real_distribution<float> dis(-2.0f, 5.0f);
+    for (auto* v : {&a, &b, &c}) for (auto& e : *v) e = cf(dis(gen), dis(gen));
+    want = c;
+    const cf alpha(1.5f, 1.0f), beta(1.5f, 3.0f);
+    for (int j = 0; j < n; ++j)
+      for (int i = 0; i < m; ++i) {
+        std::complex<double> acc = 0;
+        for (int l = 0; l < k; ++l) acc += std::complex<double>(a[l + (size_t)i * lda]) * std::complex<double>(b[l + (size_t)j * ldb]);
+        want[i + (size_t)j * ldc] = cf(std::complex<double>(alpha) * acc + std::complex<double>(beta) * std::complex<double>(c[i + (size_t)j * ldc]));
+      }
+    cf* a_u = sycl::malloc_device<cf>(a.size(), q);
+    cf* b_u = sycl::malloc_device<cf>(b.size(), q);
+    cf* c_u = sycl::malloc_device<cf>(c.size(), q);
+    helper::copy_to_device(q, a.data(), a_u, a.size());
+    helper::copy_to_device(q, b.data(), b_u, b.size());
+    helper::copy_to_device(q, c.data(), c_u, c.size());
+    sb.wait(_gemm(sb, 't', 'n', m, n, k, alpha, a_u, lda, b_u, ldb, beta, c_u, ldc));
+    std::vector<cf> got(c.size());
+    sb.wait(helper::copy_to_host(q, c_u, got.data(), got.size()));
+    sycl::free(a_u, q); sycl::free(b_u, q); sycl::free(c_u, q);
+    double worst = 0;
+    for (size_t i = 0; i < got.size(); ++i) worst = std::max(worst, (double)std::abs(got[i] - want[i]) / (std::abs(want[i]) + 1.0));
+    std::printf("%-46s max rel err %.3e  %s\n", "_gemm complex<float> tn 65x40x100", worst, worst < 2e-5 ? "PASS" : "FAIL");
+    ok &= worst < 2e-5;
+  }
+  bool threw = false;
+  try {
+    float* p = sycl::malloc_device<float>(16, q);
+    try { _symm(sb, 'l', 'x', 4, 4, 1.0f, p, 4, p, 4, 0.0f, p, 4); } catch (const std::invalid_argument& e) { threw = std::string(e.what()) == "invalid _uplo"; }
+    bool t2 = false;
+    try { _trsm(sb, 'l', 'u', 'c', 'n', 4, 4, 1.0f, p, 4, p, 4); } catch (const std::invalid_argument& e) { t2 = std::string(e.what()) == "invalid Transpose argument"; }
+    threw = threw && t2;
+    sycl::free(p, q);
+  } catch (...) { threw = false; }
+  std::printf("%-46s %s\n", "_symm / _trsm invalid arguments", threw ? "PASS" : "FAIL");
+  return ok && threw;
+}
+
 bool run_errors(blas::SB_Handle& sb) {
   auto q = sb.get_queue();
   float* p = sycl::malloc_device<float>(64, q);
@@ -149,6 +244,7 @@ int main() {
   ok &= run_gemm<sycl::half, sycl::half, AllocType::usm>(sb, 'n', 'n', 256, 128, 192, 3e-3, "_gemm half nn 256x128x192 (usm)");
   ok &= run_gemm<sycl::half, float, AllocType::buffer>(sb, 't', 'n', 125, 131, 192, 2e-5, "_gemm half->float tn 125x131x192 (buffers)");
   ok &= run_batched(sb);
+  ok &= run_symm_trsm_complex(sb);
   ok &= run_errors(sb);
   std::printf("%s\n", ok ? "ALL PASS" : "SOME FAILED");
   return ok ? 0 : 1;
