@@ -169,76 +169,85 @@ struct IlvParams {
   void* C;
   int64_t a_rs, a_cs, b_rs, b_cs;  // in elements of the *interleaved* matrix (before x batch)
   int64_t m, n, k, ldc, batch;
-  int64_t m_tiles, n_tiles;
+  int64_t m_groups, n_groups, chunks;   // block tiles along m / n, 32-entry batch chunks
   double alpha, beta;
 };
 
-template <typename TIn, typename TOut, typename TAcc, int UNROLL>
+// Every batch entry is an independent small GEMM and the batch index is the contiguous dimension, so one
+// LANE = one batch entry: every operand load of a warp is one 128-byte line, no lane ever shares data
+// with another.  A block is 32 consecutive batch entries x 8 warps; warp w owns the RM x RN register
+// tile (w % 4, w / 4) of a (4 RM) x (2 RN) block tile, so the A rows / B columns the warps of a block
+// need overlap and are served by L1 after the first touch: per K step a block fetches 4 RM + 2 RN lines
+// from L2 for 8 RM RN warp-FMAs (8x8: 48 lines per 512), instead of RM + RN per RM RN.
+// Blocks walk m fastest, then n, then the batch chunk, so neighbouring blocks re-read the same B lines
+// out of L2.
+template <typename TIn, typename TOut, typename TAcc, int RM, int RN, int UNROLL>
 __global__ void __launch_bounds__(256) gemm_interleaved_kernel(IlvParams p) {
-  // one thread = one batch entry x one 4x4 output tile; consecutive threads walk the batch
-  // index, which is the contiguous dimension of the interleaved layout.
-  const int64_t total = p.batch * p.m_tiles * p.n_tiles;
-  for (int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
-       gid += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t b = gid % p.batch;
-    const int64_t t = gid / p.batch;
-    const int64_t m0 = (t % p.m_tiles) * 4, n0 = (t / p.m_tiles) * 4;
-    const TIn* A = reinterpret_cast<const TIn*>(p.A) + b;
-    const TIn* B = reinterpret_cast<const TIn*>(p.B) + b;
-    TAcc acc[4][4];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t per_chunk = p.m_groups * p.n_groups, total = per_chunk * p.chunks;
+  for (int64_t blk = blockIdx.x; blk < total; blk += gridDim.x) {
+    const int64_t chunk = blk / per_chunk, t = blk % per_chunk;
+    const int64_t m0 = ((t % p.m_groups) * 4 + (w & 3)) * RM, n0 = ((t / p.m_groups) * 2 + (w >> 2)) * RN;
+    if (m0 >= p.m || n0 >= p.n) continue;   // warp-uniform
+    const int64_t b = chunk * 32 + lane;
+    const int64_t bc = min(b, p.batch - 1);  // lanes past the batch read entry batch-1 and store nothing
+    const TIn* A = reinterpret_cast<const TIn*>(p.A) + bc;
+    const TIn* B = reinterpret_cast<const TIn*>(p.B) + bc;
+    TAcc acc[RM][RN];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < RM; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = TAcc(0);
+      for (int j = 0; j < RN; ++j) acc[i][j] = TAcc(0);
     // rows / columns past the edge are clamped (their results are never stored): every load is
-    // unconditional, so four K steps' worth (32 loads) can be in flight per thread
-    int64_t a_off[4], b_off[4];
+    // unconditional, so UNROLL K steps' worth of loads can be in flight per thread
+    int64_t a_off[RM], b_off[RN];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) a_off[i] = min(m0 + i, p.m - 1) * p.a_rs * p.batch;
+    for (int i = 0; i < RM; ++i) a_off[i] = min(m0 + i, p.m - 1) * p.a_rs * p.batch;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) b_off[j] = min(n0 + j, p.n - 1) * p.b_cs * p.batch;
+    for (int j = 0; j < RN; ++j) b_off[j] = min(n0 + j, p.n - 1) * p.b_cs * p.batch;
     const int64_t a_kstep = p.a_cs * p.batch, b_kstep = p.b_rs * p.batch;
     int64_t kk = 0;
     for (; kk + UNROLL <= p.k; kk += UNROLL) {
-      TIn av[UNROLL][4], bv[UNROLL][4];
+      TIn av[UNROLL][RM], bv[UNROLL][RN];
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) av[u][i] = A[a_off[i] + (kk + u) * a_kstep];
+        for (int i = 0; i < RM; ++i) av[u][i] = A[a_off[i] + (kk + u) * a_kstep];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) bv[u][j] = B[b_off[j] + (kk + u) * b_kstep];
+        for (int j = 0; j < RN; ++j) bv[u][j] = B[b_off[j] + (kk + u) * b_kstep];
       }
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
-        TAcc a[4], bb[4];
+        TAcc a[RM], bb[RN];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = (TAcc)Cvt<TIn>::to_f(av[u][i]);
+        for (int i = 0; i < RM; ++i) a[i] = (TAcc)Cvt<TIn>::to_f(av[u][i]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) bb[j] = (TAcc)Cvt<TIn>::to_f(bv[u][j]);
+        for (int j = 0; j < RN; ++j) bb[j] = (TAcc)Cvt<TIn>::to_f(bv[u][j]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < RM; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], bb[j], acc[i][j]);
+          for (int j = 0; j < RN; ++j) acc[i][j] = fma(a[i], bb[j], acc[i][j]);
       }
     }
     for (; kk < p.k; ++kk) {
-      TAcc a[4], bb[4];
+      TAcc a[RM], bb[RN];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = (TAcc)Cvt<TIn>::to_f(A[a_off[i] + kk * a_kstep]);
+      for (int i = 0; i < RM; ++i) a[i] = (TAcc)Cvt<TIn>::to_f(A[a_off[i] + kk * a_kstep]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bb[j] = (TAcc)Cvt<TIn>::to_f(B[b_off[j] + kk * b_kstep]);
+      for (int j = 0; j < RN; ++j) bb[j] = (TAcc)Cvt<TIn>::to_f(B[b_off[j] + kk * b_kstep]);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < RM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], bb[j], acc[i][j]);
+        for (int j = 0; j < RN; ++j) acc[i][j] = fma(a[i], bb[j], acc[i][j]);
     }
+    if (b >= p.batch) continue;
     TOut* C = reinterpret_cast<TOut*>(p.C) + b;
     const TAcc alpha = (TAcc)p.alpha, beta = (TAcc)p.beta;
     const bool beta0 = (p.beta == 0.0);
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < RN; ++j)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < RM; ++i) {
         if (m0 + i >= p.m || n0 + j >= p.n) continue;
         TOut* dst = C + ((n0 + j) * p.ldc + (m0 + i)) * p.batch;
         TAcc r = alpha * acc[i][j];
@@ -291,7 +300,10 @@ __global__ void __launch_bounds__(256) scal_matrix_kernel(TOut* C, int64_t m, in
 }
 
 // ---- split-K epilogue ------------------------------------------------------------
-template <typename TOut, typename TAcc>
+// ws holds [batch][slice][n][m] partial sums.  VEC consecutive rows per thread (VEC = 4 needs m % 4 == 0, so a
+// vector never crosses a column; the workspace base is 256-byte aligned); the slice loop is unrolled by four so
+// that four independent loads are in flight, the sum itself keeps the fixed slice order (deterministic).
+template <typename TOut, typename TAcc, int VEC>
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const TAcc* __restrict__ ws, TOut* C,
                                                             int64_t m, int64_t n, int64_t ldc,
                                                             int64_t sc, int64_t batch, int slices,
@@ -299,17 +311,38 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const TAcc* __restri
   const TAcc alpha = (TAcc)alpha_d, beta = (TAcc)beta_d;
   const bool beta0 = (beta_d == 0.0);
   const int64_t per = m * n;
-  const int64_t total = per * batch;
+  const int64_t total = per * batch / VEC;
+  struct alignas(sizeof(TAcc) * VEC) Vec { TAcc v[VEC]; };
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t b = i / per, r = i % per;
+    const int64_t e = i * VEC;
+    const int64_t b = e / per, r = e % per;
     const TAcc* src = ws + b * slices * per + r;
-    TAcc s = TAcc(0);
-    for (int sl = 0; sl < slices; ++sl) s += src[(int64_t)sl * per];  // fixed order: deterministic
+    TAcc s[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) s[v] = TAcc(0);
+    int sl = 0;
+    for (; sl + 4 <= slices; sl += 4) {
+      Vec x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) x[u] = *reinterpret_cast<const Vec*>(src + (int64_t)(sl + u) * per);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) s[v] += x[u].v[v];
+    }
+    for (; sl < slices; ++sl) {
+      const Vec x = *reinterpret_cast<const Vec*>(src + (int64_t)sl * per);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) s[v] += x.v[v];
+    }
     TOut* dst = C + b * sc + (r % m) + (r / m) * ldc;
-    TAcc v = alpha * s;
-    if (!beta0) v += beta * (TAcc)Cvt<TOut>::to_f(*dst);
-    *dst = Cvt<TOut>::from_f(v);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      TAcc o = alpha * s[v];
+      if (!beta0) o += beta * (TAcc)Cvt<TOut>::to_f(dst[v]);
+      dst[v] = Cvt<TOut>::from_f(o);
+    }
   }
 }
 
@@ -385,22 +418,40 @@ int pbx_launch_interleaved(pbx_handle_t h, const PbxGemmCall& c) {
   p.a_rs = c.ta ? c.lda : 1; p.a_cs = c.ta ? 1 : c.lda;
   p.b_rs = c.tb ? c.ldb : 1; p.b_cs = c.tb ? 1 : c.ldb;
   p.m = c.m; p.n = c.n; p.k = c.k; p.ldc = c.ldc; p.batch = c.batch;
-  p.m_tiles = (c.m + 3) / 4; p.n_tiles = (c.n + 3) / 4;
+  p.chunks = (c.batch + 31) / 32;
   p.alpha = c.alpha; p.beta = c.beta;
-  const int64_t total = p.batch * p.m_tiles * p.n_tiles;
-  int64_t blocks = (total + 255) / 256;
-  const int64_t cap = (int64_t)h->sm_count * 32;
+  // register tile per lane: 8x8 when that still gives every SM a few blocks, else 4x4 (more, smaller blocks);
+  // fp64 stays on 4x4 (64 double accumulators would spill)
+  auto blocks_for = [&](int rm, int rn) {
+    return ((c.m + 4 * rm - 1) / (4 * rm)) * ((c.n + 2 * rn - 1) / (2 * rn)) * p.chunks;
+  };
+  static const int env_tile = getenv("PBX_ILV_TILE") ? atoi(getenv("PBX_ILV_TILE")) : 0;   // 4 or 8 (testing)
+  int tile = (c.dtype != PBX_F64 && blocks_for(8, 8) >= 2 * (int64_t)h->sm_count) ? 8 : 4;
+  if (env_tile == 4 || (env_tile == 8 && c.dtype != PBX_F64)) tile = env_tile;
+  p.m_groups = (c.m + 4 * tile - 1) / (4 * tile);
+  p.n_groups = (c.n + 2 * tile - 1) / (2 * tile);
+  int64_t blocks = p.m_groups * p.n_groups * p.chunks;
+  const int64_t cap = (int64_t)h->sm_count * 64;
   if (blocks > cap) blocks = cap;
   return dispatch_dtype(c.dtype, [&](auto* ti, auto* to, auto* ta) -> int {
     using TIn = std::remove_pointer_t<decltype(ti)>;
     using TOut = std::remove_pointer_t<decltype(to)>;
     using TAcc = std::remove_pointer_t<decltype(ta)>;
-    // K steps whose loads are issued together (in-flight loads per thread = 8 x unroll)
+    // K steps whose loads are issued together (in-flight loads per thread = (RM + RN) x unroll)
     static const int env_unroll = getenv("PBX_ILV_UNROLL") ? atoi(getenv("PBX_ILV_UNROLL")) : 0;
+    if constexpr (!std::is_same<TAcc, double>::value) {
+      if (tile == 8) {
+        if (env_unroll == 1) gemm_interleaved_kernel<TIn, TOut, TAcc, 8, 8, 1><<<(unsigned)blocks, 256, 0, h->stream>>>(p);
+        else gemm_interleaved_kernel<TIn, TOut, TAcc, 8, 8, 2><<<(unsigned)blocks, 256, 0, h->stream>>>(p);
+        h->launches++;
+        PBX_CUDA_CHECK(h, cudaGetLastError());
+        return PBX_OK;
+      }
+    }
     const int unroll = env_unroll ? env_unroll : 4;
-    if (unroll >= 4) gemm_interleaved_kernel<TIn, TOut, TAcc, 4><<<(unsigned)blocks, 256, 0, h->stream>>>(p);
-    else if (unroll >= 2) gemm_interleaved_kernel<TIn, TOut, TAcc, 2><<<(unsigned)blocks, 256, 0, h->stream>>>(p);
-    else gemm_interleaved_kernel<TIn, TOut, TAcc, 1><<<(unsigned)blocks, 256, 0, h->stream>>>(p);
+    if (unroll >= 4) gemm_interleaved_kernel<TIn, TOut, TAcc, 4, 4, 4><<<(unsigned)blocks, 256, 0, h->stream>>>(p);
+    else if (unroll >= 2) gemm_interleaved_kernel<TIn, TOut, TAcc, 4, 4, 2><<<(unsigned)blocks, 256, 0, h->stream>>>(p);
+    else gemm_interleaved_kernel<TIn, TOut, TAcc, 4, 4, 1><<<(unsigned)blocks, 256, 0, h->stream>>>(p);
     h->launches++;
     PBX_CUDA_CHECK(h, cudaGetLastError());
     return PBX_OK;
@@ -430,15 +481,21 @@ int pbx_launch_scal(pbx_handle_t h, int dtype, int64_t m, int64_t n, double beta
 }
 
 int pbx_launch_splitk_reduce(pbx_handle_t h, const PbxGemmCall& c, int slices) {
-  const int64_t total = c.m * c.n * c.batch;
+  const bool vec4 = (c.m % 4 == 0);
+  const int64_t total = c.m * c.n * c.batch / (vec4 ? 4 : 1);
   int64_t blocks = (total + 255) / 256;
   const int64_t cap = (int64_t)h->sm_count * 16;
   if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
   return dispatch_dtype(c.dtype, [&](auto* ti, auto* to, auto* ta) -> int {
     using TOut = std::remove_pointer_t<decltype(to)>;
     using TAcc = std::remove_pointer_t<decltype(ta)>;
-    splitk_reduce_kernel<TOut, TAcc><<<(unsigned)blocks, 256, 0, h->stream>>>(
-        (const TAcc*)h->ws, (TOut*)c.C, c.m, c.n, c.ldc, c.sc, c.batch, slices, c.alpha, c.beta);
+    if (vec4)
+      splitk_reduce_kernel<TOut, TAcc, 4><<<(unsigned)blocks, 256, 0, h->stream>>>(
+          (const TAcc*)h->ws, (TOut*)c.C, c.m, c.n, c.ldc, c.sc, c.batch, slices, c.alpha, c.beta);
+    else
+      splitk_reduce_kernel<TOut, TAcc, 1><<<(unsigned)blocks, 256, 0, h->stream>>>(
+          (const TAcc*)h->ws, (TOut*)c.C, c.m, c.n, c.ldc, c.sc, c.batch, slices, c.alpha, c.beta);
     h->launches++;
     PBX_CUDA_CHECK(h, cudaGetLastError());
     return PBX_OK;

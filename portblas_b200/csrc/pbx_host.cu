@@ -12,8 +12,20 @@
 // so the upload of panel j+1 and the download of panel j-1 overlap the compute of panel j
 // (H2D and D2H use separate copy engines).  Only the M x N window of C is ever written on the host
 // (2-D copies), so ld padding in the caller's buffer is preserved; C is uploaded only when beta != 0.
+//
+// Deep single GEMMs whose output is kept in the accumulate precision (fp32 / fp64 C) go one step further:
+// the scheme above cannot start computing before ALL of A has crossed PCIe, and cannot finish before the
+// last C panel has gone back.  So the column blocks shrink geometrically (n/2, n/4, ..., the last one is the
+// download tail) and the FIRST block is additionally streamed along K,
+//
+//     copy-in :  A_k0 B0_k0 | A_k1 B0_k1 | ... | A_k7 B0_k7 | B1 | B2 | B3
+//     compute :             | C0 = a A_k0 B0_k0 + b C0 | C0 += a A_k1 B0_k1 | ... | C1 | C2 | C3
+//     copy-out:                                                              | C0 | C1 | C2 | C3
+//
+// so the first MMA starts after 1/8 of A and 1/16 of B have arrived and A is resident once block 0 is done.
 #include <ctype.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "pbx_internal.cuh"
 
@@ -139,7 +151,7 @@ extern "C" int pbx_gemm_host(pbx_handle_t h, int dtype, char transa, char transb
     if (stridea < 0) return PBX_ERR_INVALID_STRIDEA;
     if (strideb < 0) return PBX_ERR_INVALID_STRIDEB;
   }
-  const int MAXP = 16;
+  const int MAXP = 32;
   int panels;
   if (batch > 1) {
     panels = (int)(batch < 8 ? batch : 8);
@@ -159,7 +171,68 @@ extern "C" int pbx_gemm_host(pbx_handle_t h, int dtype, char transa, char transb
   PBX_CUDA_CHECK(h, cudaStreamWaitEvent(h->s_in, ev_start, 0));
   PBX_CUDA_CHECK(h, cudaStreamWaitEvent(h->s_out, ev_start, 0));
 
-  if (batch == 1) {
+  static const int kstream_env = getenv("PBX_HOST_KSTREAM") ? atoi(getenv("PBX_HOST_KSTREAM")) : 1;
+  if (batch == 1 && eo >= 4 && k >= 2048 && n >= 2048 && kstream_env) {
+    // ---- K-streamed first block + geometrically shrinking column blocks ----
+    int64_t blk_n0[8], blk_nb[8];
+    int nblk = 0;
+    {
+      int64_t n0 = 0, rest = n;
+      while (rest > 0 && nblk < 7) {
+        int64_t nb = ((rest / 2) + 255) / 256 * 256;
+        if (nb < 1024 || rest - nb < 512) nb = rest;
+        blk_n0[nblk] = n0; blk_nb[nblk] = nb; ++nblk;
+        n0 += nb; rest -= nb;
+      }
+      if (rest > 0) { blk_n0[nblk] = n0; blk_nb[nblk] = rest; ++nblk; }
+    }
+    int kp_count = (int)(k / 1024);
+    if (kp_count > 8) kp_count = 8;
+    const int64_t kper = (((k + kp_count - 1) / kp_count) + 255) / 256 * 256;
+    const double one_d = 1.0;
+    const float one_f = 1.0f;
+    const void* one = (dtype == PBX_F64) ? (const void*)&one_d : (const void*)&one_f;
+    int e = 0;
+    const int64_t nb0 = blk_nb[0];
+    for (int64_t k0 = 0; k0 < k; k0 += kper) {
+      const int64_t kb = (k - k0 < kper) ? (k - k0) : kper;
+      const int64_t a_off = (ta ? k0 : k0 * lda) * es;            // op(A)[:, k0:] inside the stored matrix
+      const int64_t b_off = (tb ? k0 * ldb : k0) * es;            // op(B)[k0:, 0:nb0]
+      PBX_CUDA_CHECK(h, Copy2D::run(dA + a_off, hA + a_off, ta ? kb : m, ta ? m : kb, lda, es, cudaMemcpyHostToDevice,
+                                    h->s_in));
+      PBX_CUDA_CHECK(h, Copy2D::run(dB + b_off, hB + b_off, tb ? nb0 : kb, tb ? kb : nb0, ldb, es,
+                                    cudaMemcpyHostToDevice, h->s_in));
+      if (k0 == 0 && need_c_in)
+        PBX_CUDA_CHECK(h, Copy2D::run(dC, hC, m, nb0, ldc, eo, cudaMemcpyHostToDevice, h->s_in));
+      PBX_CUDA_CHECK(h, cudaEventRecord(ev_in[e], h->s_in));
+      PBX_CUDA_CHECK(h, cudaStreamWaitEvent(h->stream, ev_in[e], 0));
+      ++e;
+      st = pbx_gemm(h, dtype, transa, transb, m, nb0, kb, alpha, dA + a_off, lda, 0, dB + b_off, ldb, 0,
+                    k0 == 0 ? beta : one, dC, ldc, 0, 1, 0);
+      if (st != PBX_OK) { cudaStreamSynchronize(h->s_in); return st; }
+    }
+    for (int j = 0; j < nblk; ++j) {
+      const int64_t n0 = blk_n0[j], nb = blk_nb[j];
+      if (j > 0) {   // A is resident: one upload of op(B)[:, n0:n0+nb] and one full-K GEMM per block
+        const int64_t b_off = (tb ? n0 : n0 * ldb) * es;
+        PBX_CUDA_CHECK(h, Copy2D::run(dB + b_off, hB + b_off, tb ? nb : k, tb ? k : nb, ldb, es, cudaMemcpyHostToDevice,
+                                      h->s_in));
+        if (need_c_in)
+          PBX_CUDA_CHECK(h, Copy2D::run(dC + n0 * ldc * eo, hC + n0 * ldc * eo, m, nb, ldc, eo, cudaMemcpyHostToDevice,
+                                        h->s_in));
+        PBX_CUDA_CHECK(h, cudaEventRecord(ev_in[e], h->s_in));
+        PBX_CUDA_CHECK(h, cudaStreamWaitEvent(h->stream, ev_in[e], 0));
+        ++e;
+        st = pbx_gemm(h, dtype, transa, transb, m, nb, k, alpha, dA, lda, 0, dB + b_off, ldb, 0, beta,
+                      dC + n0 * ldc * eo, ldc, 0, 1, 0);
+        if (st != PBX_OK) { cudaStreamSynchronize(h->s_in); return st; }
+      }
+      PBX_CUDA_CHECK(h, cudaEventRecord(ev_done[j], h->stream));
+      PBX_CUDA_CHECK(h, cudaStreamWaitEvent(h->s_out, ev_done[j], 0));
+      PBX_CUDA_CHECK(h, Copy2D::run(hC + n0 * ldc * eo, dC + n0 * ldc * eo, m, nb, ldc, eo, cudaMemcpyDeviceToHost,
+                                    h->s_out));
+    }
+  } else if (batch == 1) {
     PBX_CUDA_CHECK(h, Copy2D::run(dA, hA, a_rows, a_cols, lda, es, cudaMemcpyHostToDevice, h->s_in));
     PBX_CUDA_CHECK(h, cudaEventRecord(ev_a, h->s_in));
     PBX_CUDA_CHECK(h, cudaStreamWaitEvent(h->stream, ev_a, 0));

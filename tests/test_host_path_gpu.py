@@ -72,3 +72,12 @@ def test_host_small_simple_path(handle):
     for (ta, tb), beta in itertools.product(TRANS, [0.0, 0.5]):
         _check(handle, torch.float32, ta, tb, 65, 33, 47, 1.5, beta, 3)
         _check(handle, torch.float64, ta, tb, 65, 33, 47, 1.5, beta, 3, batch=3)
+
+
+@pytest.mark.parametrize("tdt", [torch.float32, torch.float64])
+def test_host_k_streamed_first_block(handle, tdt):
+    """Deep single GEMM with fp32 / fp64 C: the first column block is accumulated over K panels (beta applied
+    once, then beta' = 1), later blocks run with A resident; ragged n and k, all transposes, ld padding."""
+    for (ta, tb), beta, pad in itertools.product(TRANS, [0.0, 0.5], [0, 4]):
+        _check(handle, tdt, ta, tb, 520, 2048 + 300, 2048 + 136, 1.5, beta, pad)
+    _check(handle, tdt, "n", "n", 300, 4096 + 24, 9000, -0.5, 2.0, 4)
