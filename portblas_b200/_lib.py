@@ -37,6 +37,7 @@ SYMBOLS = {
     "pbx_last_kernel": (c_int, [c_void_p]),
     "pbx_last_split_k": (c_int, [c_void_p]),
     "pbx_last_repack": (c_int, [c_void_p]),
+    "pbx_last_presplit": (c_int, [c_void_p]),
     "pbx_launch_count": (c_int64, [c_void_p]),
     "pbx_workspace_bytes": (c_int64, [c_void_p]),
     "pbx_gemm": (c_int, [c_void_p, c_int, c_char, c_char] + _GEMM_TAIL),

@@ -116,6 +116,10 @@ class SB_Handle:
         return self._lib.pbx_last_repack(self._h)
 
     @property
+    def last_presplit(self) -> int:
+        return self._lib.pbx_last_presplit(self._h)
+
+    @property
     def launch_count(self) -> int:
         return int(self._lib.pbx_launch_count(self._h))
 

@@ -282,6 +282,35 @@ __global__ void __launch_bounds__(256) repack_kernel(const T* __restrict__ src, 
   }
 }
 
+// lo half of the 3xTF32 split, computed once per operand: lo = rn_tf32(x - trunc_tf32(x)) (the tensor core reads
+// the raw fp32 word as the hi half, i.e. truncates).  Same window walk as repack_kernel, same ld / stride as the
+// source so that the lo copy shares the operand's tensor-map geometry.
+__global__ void __launch_bounds__(256) tf32_lo_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                      int64_t rows, int64_t cols, int64_t ld, int64_t stride,
+                                                      int64_t batch, int64_t chunks) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t units = batch * cols * chunks;
+  auto lo_of = [](float x) {
+    const float d = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    uint32_t lb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(d == d ? d : 0.0f));   // inf - inf -> 0
+    return __uint_as_float(lb);
+  };
+  for (int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < units; u += nwarps) {
+    const int64_t chunk = u % chunks, col = (u / chunks) % cols, b = u / (chunks * cols);
+    const int64_t r0 = chunk * 2048, r1 = min(rows, r0 + 2048);
+    const float* s = src + b * stride + col * ld;
+    float* d = dst + b * stride + col * ld;
+    int64_t r = r0 + lane;
+    for (; r + 96 < r1; r += 128) {
+      const float v0 = s[r], v1 = s[r + 32], v2 = s[r + 64], v3 = s[r + 96];
+      d[r] = lo_of(v0); d[r + 32] = lo_of(v1); d[r + 64] = lo_of(v2); d[r + 96] = lo_of(v3);
+    }
+    for (; r < r1; r += 32) d[r] = lo_of(s[r]);
+  }
+}
+
 // ---- C <- beta*C ---------------------------------------------------------------
 template <typename TOut, typename TAcc>
 __global__ void __launch_bounds__(256) scal_matrix_kernel(TOut* C, int64_t m, int64_t n, int64_t ldc,
@@ -380,6 +409,20 @@ int pbx_launch_repack(pbx_handle_t h, int elem_bytes, const void* src, void* dst
                                                                   ld_src, ld_dst, stride_src, stride_dst, batch, chunks);
   else
     return PBX_ERR_INVALID_ARG;
+  h->launches++;
+  PBX_CUDA_CHECK(h, cudaGetLastError());
+  return PBX_OK;
+}
+
+int pbx_launch_tf32_lo(pbx_handle_t h, const float* src, float* dst, int64_t rows, int64_t cols, int64_t ld,
+                       int64_t stride, int64_t batch) {
+  if (rows <= 0 || cols <= 0 || batch <= 0) return PBX_OK;
+  const int64_t chunks = (rows + 2047) / 2048;
+  const int64_t units = batch * cols * chunks;
+  int64_t blocks = (units + 7) / 8;   // 8 warps per block
+  const int64_t cap = (int64_t)h->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  tf32_lo_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(src, dst, rows, cols, ld, stride, batch, chunks);
   h->launches++;
   PBX_CUDA_CHECK(h, cudaGetLastError());
   return PBX_OK;

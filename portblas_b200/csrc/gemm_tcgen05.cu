@@ -81,7 +81,9 @@ constexpr int ROW_BYTES = 128;  // one swizzle row
 // CG = 1: one CTA computes a 128 x BN tile.  CG = 2: a CTA pair (2-CTA cluster, cta_group::2)
 // computes a 256 x BN tile; each CTA stages its own 128 rows of A and BN/2 rows of B, so the
 // shared-memory read rate per SM halves for the same MMA rate.
-template <int ES, int BN, int STAGES, int CG, int OS = 4>
+// PRE (fp32 only): the lo halves of both operands were computed by a pre-pass into global memory and arrive by
+// TMA like the raw tiles, so the CTA has no splitter warps and its shared memory carries no split traffic.
+template <int ES, int BN, int STAGES, int CG, int OS = 4, bool PRE = false>
 struct TcCfg {
   static constexpr bool TF32X3 = (ES == 4);
   static constexpr int BK = ROW_BYTES / ES;        // 64 (16-bit) or 32 (fp32) elements
@@ -103,7 +105,8 @@ struct TcCfg {
   static constexpr int ACC_STAGES = TF32X3 ? ((3 * BN <= 512) ? 2 : 1) : 2;
   static constexpr int RSUM_COL = ACC_STAGES * BN;
   static constexpr int TMEM_COLS = TF32X3 ? 512 : 2 * BN;
-  static constexpr int SPLIT_WARPS = TF32X3 ? 4 : 0;
+  static constexpr int SPLIT_WARPS = (TF32X3 && !PRE) ? 4 : 0;
+  static constexpr int TMA_BYTES = RAW_BYTES * ((TF32X3 && PRE) ? 2 : 1);   // bytes one CTA's producer lands per stage
   static constexpr int NUM_THREADS = 32 * (4 + EPI_WARPS + SPLIT_WARPS);
   static constexpr int NUM_SPLIT_THREADS = 32 * SPLIT_WARPS;
   static_assert(BN % (32 * 2) == 0 && BN <= 256 && (BN_CTA % 8) == 0, "tile width");
@@ -131,11 +134,13 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int64_t tile
 
 // M, N, ldc in TcParams are the KERNEL's view: with TRANS_OUT the caller passed (N, M) and the kernel's
 // D(row r, column c) is C(c, r), i.e. element address c + r*ldc instead of r + c*ldc.
-template <typename TIn, typename TOut, int BN, int STAGES, bool A_MN, bool B_MN, int CG, bool TRANS_OUT>
-__global__ void __launch_bounds__(TcCfg<sizeof(TIn), BN, STAGES, CG, sizeof(TOut)>::NUM_THREADS, 1)
+template <typename TIn, typename TOut, int BN, int STAGES, bool A_MN, bool B_MN, int CG, bool TRANS_OUT, bool PRE>
+__global__ void __launch_bounds__(TcCfg<sizeof(TIn), BN, STAGES, CG, sizeof(TOut), PRE>::NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const TcParams p) {
-  using Cfg = TcCfg<sizeof(TIn), BN, STAGES, CG, sizeof(TOut)>;
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAlo,
+               const __grid_constant__ CUtensorMap tmBlo, const TcParams p) {
+  using Cfg = TcCfg<sizeof(TIn), BN, STAGES, CG, sizeof(TOut), PRE>;
+  static_assert(!PRE || Cfg::TF32X3, "pre-split operands exist for fp32 only");
   constexpr bool TF32X3 = Cfg::TF32X3;
   constexpr int BK = Cfg::BK;
   constexpr int ACC_STAGES = Cfg::ACC_STAGES;
@@ -164,12 +169,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (Cfg::EPI_BYTES > 0 && p.tma_store) tma_prefetch_desc(&tmC);
+    if (PRE) { tma_prefetch_desc(&tmAlo); tma_prefetch_desc(&tmBlo); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
-      mbar_init(split_bar(s), CG * Cfg::NUM_SPLIT_THREADS + (TF32X3 ? 0 : 1));
+      mbar_init(split_bar(s), Cfg::NUM_SPLIT_THREADS > 0 ? CG * Cfg::NUM_SPLIT_THREADS : 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -191,9 +197,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      // 16-bit pair mode: both CTAs credit the leader's full barrier (the MMA issuer waits there).
-      // fp32 pair mode: each CTA's splitter warps wait on their OWN full barrier.
-      constexpr bool kLeaderFull = (CG == 2) && !TF32X3;
+      // pair mode without splitters (16-bit, pre-split fp32): both CTAs credit the leader's full barrier (the MMA
+      // issuer waits there).  fp32 with in-kernel split: each CTA's splitter warps wait on their OWN full barrier.
+      constexpr bool kLeaderFull = (CG == 2) && (!TF32X3 || PRE);
       for (int64_t tile = group; tile < p.total_tiles; tile += num_groups) {
         const TileCoord tc = decode_tile(p, tile);
         const int m0 = tc.mt * Cfg::TILE_M + (int)rank * BM;
@@ -206,8 +212,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sB = sA + Cfg::A_BYTES;
           const uint32_t fb = full_bar(stage);
-          if (kLeaderFull) { if (rank == 0) mbar_expect_tx(fb, 2 * Cfg::RAW_BYTES); }
-          else mbar_expect_tx(fb, Cfg::RAW_BYTES);
+          if (kLeaderFull) { if (rank == 0) mbar_expect_tx(fb, 2 * Cfg::TMA_BYTES); }
+          else mbar_expect_tx(fb, Cfg::TMA_BYTES);
           auto load = [&](uint32_t dst, const CUtensorMap* tm, int x, int y, int z) {
             if (kLeaderFull) tma_load_3d_2sm(dst, tm, fb, x, y, z);
             else tma_load_3d(dst, tm, fb, x, y, z);
@@ -223,6 +229,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int c = 0; c < Cfg::BN_CTA / BK; ++c) load(sB + c * BK * ROW_BYTES, &tmB, n0 + c * BK, kb * BK, zb);
           } else {
             load(sB, &tmB, kb * BK, n0, zb);
+          }
+          if (PRE) {   // lo tiles: same boxes of the pre-split copies, placed RAW_BYTES further
+            const uint32_t sAl = sA + Cfg::RAW_BYTES, sBl = sB + Cfg::RAW_BYTES;
+            if (A_MN) {
+#pragma unroll
+              for (int c = 0; c < BM / BK; ++c) load(sAl + c * BK * ROW_BYTES, &tmAlo, m0 + c * BK, kb * BK, za);
+            } else {
+              load(sAl, &tmAlo, kb * BK, m0, za);
+            }
+            if (B_MN) {
+#pragma unroll
+              for (int c = 0; c < Cfg::BN_CTA / BK; ++c)
+                load(sBl + c * BK * ROW_BYTES, &tmBlo, n0 + c * BK, kb * BK, zb);
+            } else {
+              load(sBl, &tmBlo, kb * BK, n0, zb);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -260,9 +282,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
           for (int kb = kc0; kb < kc1; ++kb) {
-            const uint32_t ready = TF32X3 ? split_bar(stage) : full_bar(stage);
-            // fp32 pair mode: the peer's splitter warps wrote shared memory with ordinary stores
-            if (CG == 2 && TF32X3) mbar_wait_cluster(ready, phase); else mbar_wait(ready, phase);
+            constexpr bool kSplit = TF32X3 && !PRE;
+            const uint32_t ready = kSplit ? split_bar(stage) : full_bar(stage);
+            // fp32 pair mode with in-kernel split: the peer's splitter warps wrote shared memory with ordinary stores
+            if (CG == 2 && kSplit) mbar_wait_cluster(ready, phase); else mbar_wait(ready, phase);
             tc_fence_after();
             const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
             const uint32_t sB = sA + Cfg::A_BYTES;
@@ -459,7 +482,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (OUT16 && tma_store && lane == 0) bulk_wait_read<0>();   // staging tiles must outlive their stores
     __syncwarp();
-  } else if (TF32X3 && warp >= 4 + Cfg::EPI_WARPS) {
+  } else if (TF32X3 && !PRE && warp >= 4 + Cfg::EPI_WARPS) {
     // ===================== fp32 -> (hi, lo) tf32 splitters (each CTA splits what it staged) ==============
     const int st = threadIdx.x - 32 * (4 + Cfg::EPI_WARPS);
     int stage = 0;
@@ -576,12 +599,15 @@ bool make_c_map(CUtensorMap* out, int es, CUtensorMapDataType dt, void* ptr, int
   return r == CUDA_SUCCESS;
 }
 
-template <typename TIn, typename TOut, int BN, int STAGES, bool A_MN, bool B_MN, int CG, bool TRANS_OUT>
-int launch_inst(pbx_handle_t h, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
-                const TcParams& p) {
-  using Cfg = TcCfg<sizeof(TIn), BN, STAGES, CG, sizeof(TOut)>;
+struct TcMaps {
+  CUtensorMap a, b, c, alo, blo;
+};
+
+template <typename TIn, typename TOut, int BN, int STAGES, bool A_MN, bool B_MN, int CG, bool TRANS_OUT, bool PRE>
+int launch_inst(pbx_handle_t h, const TcMaps& tm, const TcParams& p) {
+  using Cfg = TcCfg<sizeof(TIn), BN, STAGES, CG, sizeof(TOut), PRE>;
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared memory budget");
-  auto kern = gemm_tc_kernel<TIn, TOut, BN, STAGES, A_MN, B_MN, CG, TRANS_OUT>;
+  auto kern = gemm_tc_kernel<TIn, TOut, BN, STAGES, A_MN, B_MN, CG, TRANS_OUT, PRE>;
   static bool attr_set[16] = {};   // per device ordinal: the attribute is sticky, set it once
   if (h->device >= 16 || !attr_set[h->device]) {
     PBX_CUDA_CHECK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -601,32 +627,38 @@ int launch_inst(pbx_handle_t h, const CUtensorMap& tmA, const CUtensorMap& tmB, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  PBX_CUDA_CHECK(h, cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, p));
+  PBX_CUDA_CHECK(h, cudaLaunchKernelEx(&cfg, kern, tm.a, tm.b, tm.c, tm.alo, tm.blo, p));
   h->launches++;
   return PBX_OK;
 }
 
-template <typename TIn, typename TOut, int BN, int STAGES, int CG, bool TRANS_OUT = false>
-int launch_major(pbx_handle_t h, bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                 const CUtensorMap& tmC, const TcParams& p) {
+template <typename TIn, typename TOut, int BN, int STAGES, int CG, bool TRANS_OUT, bool PRE>
+int launch_major(pbx_handle_t h, bool a_mn, bool b_mn, const TcMaps& tm, const TcParams& p) {
   if (a_mn) {
-    return b_mn ? launch_inst<TIn, TOut, BN, STAGES, true, true, CG, TRANS_OUT>(h, tmA, tmB, tmC, p)
-                : launch_inst<TIn, TOut, BN, STAGES, true, false, CG, TRANS_OUT>(h, tmA, tmB, tmC, p);
+    return b_mn ? launch_inst<TIn, TOut, BN, STAGES, true, true, CG, TRANS_OUT, PRE>(h, tm, p)
+                : launch_inst<TIn, TOut, BN, STAGES, true, false, CG, TRANS_OUT, PRE>(h, tm, p);
   }
-  return b_mn ? launch_inst<TIn, TOut, BN, STAGES, false, true, CG, TRANS_OUT>(h, tmA, tmB, tmC, p)
-              : launch_inst<TIn, TOut, BN, STAGES, false, false, CG, TRANS_OUT>(h, tmA, tmB, tmC, p);
+  return b_mn ? launch_inst<TIn, TOut, BN, STAGES, false, true, CG, TRANS_OUT, PRE>(h, tm, p)
+              : launch_inst<TIn, TOut, BN, STAGES, false, false, CG, TRANS_OUT, PRE>(h, tm, p);
 }
 
 // tile configurations, most efficient first: CTA pair 256x256, CTA pair 256x128, single CTA 128x128;
 // bn == 64 is the skinny-M configuration (operands swapped, 128 columns of C x 64 rows per tile)
-template <typename TIn, typename TOut>
-int launch_cfg(pbx_handle_t h, int cg, int bn, bool a_mn, bool b_mn, const CUtensorMap& tmA,
-               const CUtensorMap& tmB, const CUtensorMap& tmC, const TcParams& p) {
+template <typename TIn, typename TOut, bool PRE>
+int launch_cfg_pre(pbx_handle_t h, int cg, int bn, bool a_mn, bool b_mn, const TcMaps& tm, const TcParams& p) {
   constexpr bool F32 = sizeof(TIn) == 4;
-  if (bn == 64) return launch_major<TIn, TOut, 64, F32 ? 4 : 8, 1, true>(h, a_mn, b_mn, tmA, tmB, tmC, p);  // swapped operands
-  if (cg == 2 && bn == 256) return launch_major<TIn, TOut, 256, F32 ? 3 : 6, 2>(h, a_mn, b_mn, tmA, tmB, tmC, p);
-  if (cg == 2) return launch_major<TIn, TOut, 128, F32 ? 4 : 8, 2>(h, a_mn, b_mn, tmA, tmB, tmC, p);
-  return launch_major<TIn, TOut, 128, F32 ? 3 : 6, 1>(h, a_mn, b_mn, tmA, tmB, tmC, p);
+  if (bn == 64) return launch_major<TIn, TOut, 64, F32 ? 4 : 8, 1, true, PRE>(h, a_mn, b_mn, tm, p);  // swapped operands
+  if (cg == 2 && bn == 256) return launch_major<TIn, TOut, 256, F32 ? 3 : 6, 2, false, PRE>(h, a_mn, b_mn, tm, p);
+  if (cg == 2) return launch_major<TIn, TOut, 128, F32 ? 4 : 8, 2, false, PRE>(h, a_mn, b_mn, tm, p);
+  return launch_major<TIn, TOut, 128, F32 ? 3 : 6, 1, false, PRE>(h, a_mn, b_mn, tm, p);
+}
+
+template <typename TIn, typename TOut>
+int launch_cfg(pbx_handle_t h, int cg, int bn, bool a_mn, bool b_mn, bool pre, const TcMaps& tm, const TcParams& p) {
+  if constexpr (sizeof(TIn) == 4) {
+    if (pre) return launch_cfg_pre<TIn, TOut, true>(h, cg, bn, a_mn, b_mn, tm, p);
+  }
+  return launch_cfg_pre<TIn, TOut, false>(h, cg, bn, a_mn, b_mn, tm, p);
 }
 
 struct TcPlan {
@@ -732,12 +764,48 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
   Opnd X = {c.A, c.m, c.lda, c.sa, !c.ta}, Y = {c.B, c.n, c.ldb, c.sb, c.tb};
   if (plan.swap) { Opnd t = X; X = Y; Y = t; }
   const bool a_mn = X.mn_major, b_mn = Y.mn_major;
-  CUtensorMap tmA, tmB;
-  if (!make_operand_map(&tmA, es, dt, X.p, X.mn, c.k, X.ld, c.batch, X.st, !a_mn, BM) ||
-      !make_operand_map(&tmB, es, dt, Y.p, Y.mn, c.k, Y.ld, c.batch, Y.st, !b_mn, bn / cg)) {
+  // fp32, compute-bound shapes: split the lo halves of both operands ONCE into pooled global buffers (one
+  // HBM-bound pass each) instead of once per tile in shared memory.  The in-kernel splitters read and rewrite
+  // every staged tile, which together with the three tf32 MMAs' operand reads oversubscribes the 128 B/clk of
+  // shared memory (measured: tensor pipe 68 % active at 16384^3); with the lo tiles arriving by TMA the
+  // mainloop's shared-memory traffic drops by a quarter and the CTA needs no splitter warps.  Memory-bound
+  // shapes (arithmetic intensity < 256 flop/B) keep the in-kernel split: the pre-pass would triple their traffic.
+  bool pre = false;
+  const void* lo_ptr[2] = {nullptr, nullptr};
+  if (f32) {
+    const int pre_env = getenv("PBX_TF32_PRESPLIT") ? atoi(getenv("PBX_TF32_PRESPLIT")) : -1;
+    const double flops = 2.0 * (double)c.m * (double)c.n * (double)c.k * (double)c.batch;
+    const double byts = 4.0 * ((double)c.m * c.k + (double)c.k * c.n + (double)c.m * c.n) * (double)c.batch;
+    pre = (pre_env >= 0) ? (pre_env != 0) : (flops >= 5e8 && flops / byts >= 256.0);
+    if (pre) {
+      const Opnd* ops[2] = {&X, &Y};
+      for (int i = 0; i < 2 && pre; ++i) {
+        const Opnd& o = *ops[i];
+        const int64_t rows = o.mn_major ? o.mn : c.k, cols = o.mn_major ? c.k : o.mn;
+        const int64_t copies = (c.batch > 1 && o.st > 0) ? c.batch : 1;
+        const int64_t elems = (copies - 1) * o.st + o.ld * cols;
+        if (pbx_ensure_lo(h, i, elems * 4) != PBX_OK ||
+            pbx_launch_tf32_lo(h, (const float*)o.p, (float*)h->lo[i], rows, cols, o.ld, o.st, copies) != PBX_OK) {
+          pre = false;   // no room for the copies: fall back to the in-kernel split
+          break;
+        }
+        lo_ptr[i] = h->lo[i];
+      }
+    }
+  }
+  TcMaps tm;
+  if (!make_operand_map(&tm.a, es, dt, X.p, X.mn, c.k, X.ld, c.batch, X.st, !a_mn, BM) ||
+      !make_operand_map(&tm.b, es, dt, Y.p, Y.mn, c.k, Y.ld, c.batch, Y.st, !b_mn, bn / cg)) {
     h->last_error = "cuTensorMapEncodeTiled failed";
     return PBX_ERR_CUDA;
   }
+  tm.alo = tm.a; tm.blo = tm.b;   // placeholders when unused (never dereferenced)
+  if (pre && (!make_operand_map(&tm.alo, es, dt, lo_ptr[0], X.mn, c.k, X.ld, c.batch, X.st, !a_mn, BM) ||
+              !make_operand_map(&tm.blo, es, dt, lo_ptr[1], Y.mn, c.k, Y.ld, c.batch, Y.st, !b_mn, bn / cg))) {
+    h->last_error = "cuTensorMapEncodeTiled failed";
+    return PBX_ERR_CUDA;
+  }
+  h->last_presplit = pre ? 1 : 0;
   TcParams p;
   p.C = c.C; p.ws = (float*)h->ws;
   p.M = X.mn; p.N = Y.mn; p.K = c.k; p.ldc = c.ldc; p.sc = c.sc;
@@ -762,22 +830,22 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
   p.total_tiles = (int64_t)p.m_tiles * p.n_tiles * c.batch * slices;
 
   // 16-bit C with beta == 0 leaves through shared memory + TMA stores when C is TMA-legal
-  CUtensorMap tmC = tmA;  // placeholder when unused (never dereferenced)
+  tm.c = tm.a;  // placeholder when unused (never dereferenced)
   p.tma_store = 0;
   const bool out16 = (c.dtype == PBX_F16 || c.dtype == PBX_BF16);
   const char* ts_env = getenv("PBX_TMA_STORE");
   if (out16 && c.beta == 0.0 && slices == 1 && !(ts_env && atoi(ts_env) == 0) && ((uintptr_t)c.C % 16 == 0) &&
       (c.ldc * 2) % 16 == 0 && (c.batch == 1 || (c.sc * 2) % 16 == 0) && c.ldc * 2 < ((int64_t)1 << 40) &&
       c.sc * 2 < ((int64_t)1 << 40)) {
-    if (make_c_map(&tmC, 2, dt, c.C, c.m, c.n, c.ldc, c.batch, c.sc)) p.tma_store = 1;
+    if (make_c_map(&tm.c, 2, dt, c.C, c.m, c.n, c.ldc, c.batch, c.sc)) p.tma_store = 1;
   }
 
   switch (c.dtype) {
-    case PBX_F32: return launch_cfg<float, float>(h, cg, bn, a_mn, b_mn, tmA, tmB, tmC, p);
-    case PBX_F16: return launch_cfg<__half, __half>(h, cg, bn, a_mn, b_mn, tmA, tmB, tmC, p);
-    case PBX_F16_F32: return launch_cfg<__half, float>(h, cg, bn, a_mn, b_mn, tmA, tmB, tmC, p);
-    case PBX_BF16: return launch_cfg<__nv_bfloat16, __nv_bfloat16>(h, cg, bn, a_mn, b_mn, tmA, tmB, tmC, p);
-    case PBX_BF16_F32: return launch_cfg<__nv_bfloat16, float>(h, cg, bn, a_mn, b_mn, tmA, tmB, tmC, p);
+    case PBX_F32: return launch_cfg<float, float>(h, cg, bn, a_mn, b_mn, pre, tm, p);
+    case PBX_F16: return launch_cfg<__half, __half>(h, cg, bn, a_mn, b_mn, pre, tm, p);
+    case PBX_F16_F32: return launch_cfg<__half, float>(h, cg, bn, a_mn, b_mn, pre, tm, p);
+    case PBX_BF16: return launch_cfg<__nv_bfloat16, __nv_bfloat16>(h, cg, bn, a_mn, b_mn, pre, tm, p);
+    case PBX_BF16_F32: return launch_cfg<__nv_bfloat16, float>(h, cg, bn, a_mn, b_mn, pre, tm, p);
   }
   return PBX_ERR_INVALID_ARG;
 }

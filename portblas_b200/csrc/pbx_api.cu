@@ -76,6 +76,8 @@ int pbx_destroy(pbx_handle_t h) {
     if (h->pack[i]) cudaFree(h->pack[i]);
   for (int i = 0; i < 4; ++i)
     if (h->aux[i]) cudaFree(h->aux[i]);
+  for (int i = 0; i < 2; ++i)
+    if (h->lo[i]) cudaFree(h->lo[i]);
   for (cudaEvent_t e : h->events) cudaEventDestroy(e);
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_out) cudaStreamDestroy(h->s_out);
@@ -98,6 +100,7 @@ int pbx_set_split_k(pbx_handle_t h, int s) { if (!h || s < 0) return PBX_ERR_INV
 int pbx_last_kernel(pbx_handle_t h) { return h ? h->last_kernel : PBX_KERNEL_NONE; }
 int pbx_last_split_k(pbx_handle_t h) { return h ? h->last_split_k : 0; }
 int pbx_last_repack(pbx_handle_t h) { return h ? h->last_repack : 0; }
+int pbx_last_presplit(pbx_handle_t h) { return h ? h->last_presplit : 0; }
 int64_t pbx_launch_count(pbx_handle_t h) { return h ? h->launches : 0; }
 int64_t pbx_workspace_bytes(pbx_handle_t h) { return h ? h->ws_bytes : 0; }
 
@@ -140,6 +143,19 @@ int pbx_ensure_aux(pbx_handle_t h, int i, int64_t bytes) {
     return PBX_ERR_WORKSPACE;
   }
   h->aux_bytes[i] = rounded;
+  return PBX_OK;
+}
+
+int pbx_ensure_lo(pbx_handle_t h, int i, int64_t bytes) {
+  if (i < 0 || i >= 2) return PBX_ERR_INVALID_ARG;
+  if (bytes <= h->lo_bytes[i]) return PBX_OK;
+  if (h->lo[i]) {
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaFree(h->lo[i]) != cudaSuccess) return PBX_ERR_WORKSPACE;
+    h->lo[i] = nullptr; h->lo_bytes[i] = 0;
+  }
+  const int64_t rounded = ((bytes + (1 << 20) - 1) >> 20) << 20;
+  if (cudaMalloc(&h->lo[i], (size_t)rounded) != cudaSuccess) { cudaGetLastError(); return PBX_ERR_WORKSPACE; }
+  h->lo_bytes[i] = rounded;
   return PBX_OK;
 }
 
@@ -245,6 +261,7 @@ static int run_gemm(pbx_handle_t h, const PbxGemmCall& c_in, int batch_type) {
 
   h->last_kernel = kernel;
   h->last_split_k = 1;
+  h->last_presplit = 0;
   int st = PBX_OK;
   if (kernel == PBX_KERNEL_INTERLEAVED) return pbx_launch_interleaved(h, c);
 

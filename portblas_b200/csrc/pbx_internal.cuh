@@ -46,6 +46,10 @@ struct pbx_handle_s {
   // aligned copies of TMA-illegal operands (pbx_api.cu: repack_for_tma); grow monotonically
   void* pack[2] = {nullptr, nullptr};
   int64_t pack_bytes[2] = {0, 0};
+  // fp32 pre-split: lo halves (tf32) of A and B computed once per call (gemm_tcgen05.cu); grow monotonically
+  void* lo[2] = {nullptr, nullptr};
+  int64_t lo_bytes[2] = {0, 0};
+  int last_presplit = 0;
   // pooled temporaries of the GEMM-built routines (blas3_ext.cu: symmetrised A, planar complex operands,
   // inverted diagonal blocks / X of trsm); grow monotonically, stream ordered
   void* aux[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -87,6 +91,10 @@ static inline size_t pbx_out_size(int dtype) {
 
 int pbx_ensure_workspace(pbx_handle_t h, int64_t bytes);
 int pbx_ensure_aux(pbx_handle_t h, int i, int64_t bytes);
+int pbx_ensure_lo(pbx_handle_t h, int i, int64_t bytes);
+// lo = rn_tf32(x - trunc_tf32(x)) over a rows x cols column-major window (x batch), same ld / stride as the source
+int pbx_launch_tf32_lo(pbx_handle_t h, const float* src, float* dst, int64_t rows, int64_t cols, int64_t ld,
+                       int64_t stride, int64_t batch);
 
 // ---- kernel families (each returns a pbx_status_t) -----------------------
 // slices > 1: the kernel writes raw fp32/fp64 partial sums to h->ws laid out

@@ -292,3 +292,46 @@ def test_golden_fixtures_gpu(handle):
         handle.wait()
         got = c.to(torch.float64 if dt == "f64" else torch.float32).cpu().numpy()
         assert oracle.compare(got, g[f"case{i}_out"], kind) == 0, f"golden case {i} ({dt} {ta}{tb} {m}x{n}x{k})"
+
+
+def test_fp32_presplit_operands(handle):
+    """fp32 with the lo halves of A and B pre-split in global memory (PBX_TF32_PRESPLIT=1, the default for
+    compute-bound shapes) must agree with the in-kernel split on every tile configuration, transpose, ragged
+    edge, strided batch (incl. stride-0 broadcast), K slice count, the skinny-M operand swap and repacked
+    (odd-ld) operands; and a large square shape must pick it on its own."""
+    pre = ("PBX_TF32_PRESPLIT", "1")
+    cases = []
+    for cfg in ("1,128", "2,128", "2,256"):
+        env = (pre, ("PBX_TC_CONFIG", cfg))
+        for (ta, tb), be in itertools.product(TRANS, [0.0, 0.5]):
+            cases.append(Case(dtype="f32", transa=ta, transb=tb, m=392, n=520, k=1096, alpha=1.5, beta=be,
+                              kernel=TCGEN05, env=env))
+        cases.append(Case(dtype="f32", m=300, n=260, k=4104, alpha=1.0, beta=0.5, kernel=TCGEN05, split_k=3, env=env))
+        cases.append(Case(dtype="f32", api="strided", transa="t", m=264, n=392, k=200, alpha=1.0, beta=0.0, batch=5,
+                          stride_a_mul=0, kernel=TCGEN05, env=env))
+        cases.append(Case(dtype="f32", api="strided", transb="t", m=264, n=136, k=328, alpha=-1.0, beta=1.0, batch=4,
+                          stride_b_mul=2, stride_c_mul=2, kernel=TCGEN05, env=env))
+    for (ta, tb) in TRANS:   # skinny-M swap and odd-ld repack under the pre-split
+        cases.append(Case(dtype="f32", transa=ta, transb=tb, m=40, n=1000, k=520, alpha=1.5, beta=0.5, kernel=TCGEN05,
+                          env=(pre,)))
+        cases.append(Case(dtype="f32", transa=ta, transb=tb, m=263, n=131, k=517, alpha=1.5, beta=0.5, offset=1,
+                          kernel=TCGEN05, env=(pre,)))
+    cases.append(Case(dtype="f32", m=512, n=512, k=65536, alpha=1.0, beta=0.0, env=(pre,)))
+    _run_all(handle, cases)
+    # auto selection on a compute-bound shape, checked on the device against an fp64 product
+    import torch
+    from portblas_b200 import blas
+    n = 2048
+    g = torch.Generator(device="cuda").manual_seed(7)
+    a = torch.rand(n * n, device="cuda", generator=g) * 7 - 2
+    b = torch.rand(n * n, device="cuda", generator=g) * 7 - 2
+    c = torch.zeros(n * n, device="cuda")
+    blas._gemm(handle, "n", "t", n, n, n, 1.0, a, n, b, n, 0.0, c, n)
+    handle.wait()
+    assert handle.last_kernel == "tcgen05" and handle.last_presplit == 1
+    A, B = a.view(n, n).T.double(), b.view(n, n).T.double()          # column-major -> (rows, cols)
+    want = A @ B.T
+    bound = A.abs() @ B.abs().T
+    assert float(((c.view(n, n).T.double() - want).abs() / bound).max()) <= 1e-5
+    r = run_case(handle, Case(dtype="f32", m=512, n=512, k=65536, alpha=1.0, beta=0.0))   # AI 127: stays in-kernel
+    assert r.ok and handle.last_presplit == 0
