@@ -326,6 +326,9 @@ def main():
     if args.gather and world > 1:
         torch.cuda.synchronize()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        warm = torch.zeros(1 << 20, device=dev, dtype=tdt)      # NCCL channel set-up happens on the first collective
+        dist.all_gather_into_tensor(torch.empty(world << 20, device=dev, dtype=tdt), warm)
+        torch.cuda.synchronize()
         dist.barrier()
         g0.record()
         if batch == 1 and strong:

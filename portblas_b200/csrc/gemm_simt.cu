@@ -257,6 +257,109 @@ __global__ void __launch_bounds__(256) gemm_interleaved_kernel(IlvParams p) {
   }
 }
 
+// fp32 interleaved batches, shared-memory staged.  Same mapping as gemm_interleaved_kernel (lane = batch entry, warp
+// (w % 4, w / 4) owns an RM x RN register tile of a (4 RM) x (2 RN) block tile), but the 4 RM + 2 RN operand lines a block
+// needs per k are fetched ONCE by cp.async into a STAGES-deep ring (KB k-steps per stage) and read back conflict-free
+// (a warp reads 32 consecutive floats), so L2 sees every line once per block instead of once per warp and the loads of
+// later stages fly under the FMAs.  Out-of-range rows / columns / lanes are clamped (never stored), the K tail is
+// zero-filled through the cp.async source size.
+template <int RM, int RN, int KB, int STAGES>
+__global__ void __launch_bounds__(256, 2) gemm_interleaved_f32_smem_kernel(IlvParams p) {
+  constexpr int TM = 4 * RM, TN = 2 * RN, ROWS = TM + TN, RPW = ROWS / 8;
+  static_assert(ROWS % 8 == 0, "rows are dealt to the 8 warps");
+  extern __shared__ __align__(16) float ilv_smem[];   // [STAGES][KB][ROWS][32]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int wm = w & 3, wn = w >> 2;
+  const float* Ag = reinterpret_cast<const float*>(p.A);
+  const float* Bg = reinterpret_cast<const float*>(p.B);
+  const int64_t per_chunk = p.m_groups * p.n_groups, total = per_chunk * p.chunks;
+  const int nk = (int)((p.k + KB - 1) / KB);
+  const int64_t a_kstep = p.a_cs * p.batch, b_kstep = p.b_rs * p.batch;
+  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(ilv_smem);
+  for (int64_t blk = blockIdx.x; blk < total; blk += gridDim.x) {
+    const int64_t chunk = blk / per_chunk, t = blk % per_chunk;
+    const int64_t m_base = (t % p.m_groups) * TM, n_base = (t / p.m_groups) * TN;
+    const int64_t b = chunk * 32 + lane;
+    const int64_t bc = min(b, p.batch - 1);
+    // the RPW operand rows this warp fetches: block row r = w + 8 j is an A row (r < TM) or a B column
+    const float* rbase[RPW];
+    int64_t rstep[RPW];
+#pragma unroll
+    for (int j = 0; j < RPW; ++j) {
+      const int r = w + 8 * j;
+      if (r < TM) {
+        rbase[j] = Ag + min(m_base + r, p.m - 1) * p.a_rs * p.batch + bc;
+        rstep[j] = a_kstep;
+      } else {
+        rbase[j] = Bg + min(n_base + (r - TM), p.n - 1) * p.b_cs * p.batch + bc;
+        rstep[j] = b_kstep;
+      }
+    }
+    auto issue = [&](int ks, int stage) {
+      const uint32_t sdst = smem0 + (uint32_t)(stage * KB * ROWS * 32 + lane) * 4u;
+#pragma unroll
+      for (int kk = 0; kk < KB; ++kk) {
+        const int64_t kg = (int64_t)ks * KB + kk;
+        const uint32_t nbytes = kg < p.k ? 4u : 0u;        // K tail: zero fill
+        const int64_t kc = min(kg, p.k - 1);
+#pragma unroll
+        for (int j = 0; j < RPW; ++j) {
+          const uint32_t d = sdst + (uint32_t)((kk * ROWS + w + 8 * j) * 32) * 4u;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(rbase[j] + kc * rstep[j]), "r"(nbytes)
+                       : "memory");
+        }
+      }
+    };
+    float acc[RM][RN];
+#pragma unroll
+    for (int i = 0; i < RM; ++i)
+#pragma unroll
+      for (int j = 0; j < RN; ++j) acc[i][j] = 0.0f;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+      if (s < nk) issue(s, s);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int ks = 0; ks < nk; ++ks) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 2) : "memory");
+      __syncthreads();   // stage ks has landed for every warp; stage ks-1 is no longer being read
+      const int nxt = ks + STAGES - 1;
+      if (nxt < nk) issue(nxt, nxt % STAGES);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      const float* st = ilv_smem + (size_t)(ks % STAGES) * KB * ROWS * 32 + lane;
+#pragma unroll
+      for (int kk = 0; kk < KB; ++kk) {
+        float a[RM], bb[RN];
+#pragma unroll
+        for (int i = 0; i < RM; ++i) a[i] = st[(kk * ROWS + wm * RM + i) * 32];
+#pragma unroll
+        for (int j = 0; j < RN; ++j) bb[j] = st[(kk * ROWS + TM + wn * RN + j) * 32];
+#pragma unroll
+        for (int i = 0; i < RM; ++i)
+#pragma unroll
+          for (int j = 0; j < RN; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();   // the ring is reused by the next block tile
+    const int64_t m0 = m_base + wm * RM, n0 = n_base + wn * RN;
+    if (b >= p.batch || m0 >= p.m || n0 >= p.n) continue;
+    float* C = reinterpret_cast<float*>(p.C) + b;
+    const float alpha = (float)p.alpha, beta = (float)p.beta;
+    const bool beta0 = (p.beta == 0.0);
+#pragma unroll
+    for (int j = 0; j < RN; ++j)
+#pragma unroll
+      for (int i = 0; i < RM; ++i) {
+        if (m0 + i >= p.m || n0 + j >= p.n) continue;
+        float* dst = C + ((n0 + j) * p.ldc + (m0 + i)) * p.batch;
+        float r = alpha * acc[i][j];
+        if (!beta0) r += beta * *dst;
+        *dst = r;
+      }
+  }
+}
+
 // ---- operand re-layout -----------------------------------------------------------
 // rows x cols column-major window (x batch) copied to a new leading dimension / batch stride, so
 // that an operand with an odd ld or a base that is not 16-byte aligned becomes TMA-legal.  One warp
@@ -476,6 +579,24 @@ int pbx_launch_interleaved(pbx_handle_t h, const PbxGemmCall& c) {
   int64_t blocks = p.m_groups * p.n_groups * p.chunks;
   const int64_t cap = (int64_t)h->sm_count * 64;
   if (blocks > cap) blocks = cap;
+  static const int env_smem = getenv("PBX_ILV_SMEM") ? atoi(getenv("PBX_ILV_SMEM")) : 1;
+  if (c.dtype == PBX_F32 && env_smem) {   // shared-memory staged ring (fp32)
+    constexpr int KB = 4, STAGES = 4;
+    if (tile == 8) {
+      constexpr int SMEM = STAGES * KB * (4 * 8 + 2 * 8) * 32 * 4;
+      auto kern = gemm_interleaved_f32_smem_kernel<8, 8, KB, STAGES>;
+      PBX_CUDA_CHECK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+      kern<<<(unsigned)blocks, 256, SMEM, h->stream>>>(p);
+    } else {
+      constexpr int SMEM = STAGES * KB * (4 * 4 + 2 * 4) * 32 * 4;
+      auto kern = gemm_interleaved_f32_smem_kernel<4, 4, KB, STAGES>;
+      PBX_CUDA_CHECK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+      kern<<<(unsigned)blocks, 256, SMEM, h->stream>>>(p);
+    }
+    h->launches++;
+    PBX_CUDA_CHECK(h, cudaGetLastError());
+    return PBX_OK;
+  }
   return dispatch_dtype(c.dtype, [&](auto* ti, auto* to, auto* ta) -> int {
     using TIn = std::remove_pointer_t<decltype(ti)>;
     using TOut = std::remove_pointer_t<decltype(to)>;

@@ -70,6 +70,13 @@ def gather_c_mblocks(c_local: torch.Tensor, m: int, n: int, world: int, align: i
     m x n column-major matrix on every rank."""
     shapes = [split_range(m, world, r, align) for r in range(world)]
     max_rows = max(s[1] for s in shapes)
+    if all(s[1] == max_rows for s in shapes) and hasattr(dist, "all_gather_into_tensor"):
+        # equal blocks: one all-gather straight into a [world][n][rows] staging tensor, then one strided copy
+        stage = torch.empty(world * n * max_rows, dtype=c_local.dtype, device=c_local.device)
+        dist.all_gather_into_tensor(stage, c_local[:n * max_rows].contiguous(), group=group)
+        full = torch.empty(m * n, dtype=c_local.dtype, device=c_local.device)
+        full.view(n, world, max_rows).copy_(stage.view(world, n, max_rows).permute(1, 0, 2))
+        return full
     pad = torch.zeros(max_rows * n, dtype=c_local.dtype, device=c_local.device)
     rows = shapes[dist.get_rank(group)][1]
     pad.view(n, max_rows)[:, :rows] = c_local.view(n, rows)
@@ -87,6 +94,11 @@ def gather_c_batches(c_local: torch.Tensor, per_matrix: int, batch: int, world: 
     """All-gather contiguous batch ranges of C (stride_c == per_matrix)."""
     shapes = [split_range(batch, world, r) for r in range(world)]
     max_b = max(s[1] for s in shapes)
+    if all(s[1] == max_b for s in shapes) and hasattr(dist, "all_gather_into_tensor"):
+        # equal batch ranges: the concatenation of the shards IS the full buffer -- one all-gather, no copies
+        full = torch.empty(batch * per_matrix, dtype=c_local.dtype, device=c_local.device)
+        dist.all_gather_into_tensor(full, c_local[:max_b * per_matrix].contiguous(), group=group)
+        return full
     pad = torch.zeros(max_b * per_matrix, dtype=c_local.dtype, device=c_local.device)
     cnt = shapes[dist.get_rank(group)][1]
     pad[:cnt * per_matrix] = c_local[:cnt * per_matrix]
