@@ -80,6 +80,9 @@ def roofline_for(w, avg_ms, traffic):
         tensor_peak = NOMINAL_FP64_TFLOPS
         src = ("nominal fp64 40 TF (no fp64 entry in MEASURED_PEAKS.json); measured DMMA pipe ceiling "
                f"{MEASURED_FP64_PIPE_TFLOPS} TF (tools/micro/dmma_rate.cu, profiles/r01/dmma_rate.txt)")
+    elif w["dt"] == "f32" and os.environ.get("SB_ENABLE_JOINT_MATRIX", "")[:1] == "1":
+        tensor_peak = pk["bf16"] / 2.0
+        src = f"single-tf32 roof (SB_ENABLE_JOINT_MATRIX=1: reduced-precision fragments) = bf16 {pk['source']} / 2"
     elif w["dt"] == "f32":
         tensor_peak = pk["bf16"] / 2.0 / 3.0
         src = f"3xTF32 roof = bf16 {pk['source']} / 2 (tf32 rate) / 3 (three MMAs per product)"
@@ -96,7 +99,8 @@ def roofline_for(w, avg_ms, traffic):
     if w["dt"] != "f64" and pk.get("bf16_sustained"):
         # a kernel that runs for tens of milliseconds back to back sits at the board's power cap: the same ratio
         # against the SUSTAINED bf16 figure of MEASURED_PEAKS.json (burst stays the headline `peak` / `frac`)
-        sus = pk["bf16_sustained"] / (6.0 if w["dt"] == "f32" else 1.0)
+        div = 1.0 if w["dt"] != "f32" else (2.0 if os.environ.get("SB_ENABLE_JOINT_MATRIX", "")[:1] == "1" else 6.0)
+        sus = pk["bf16_sustained"] / div
         out["peak_sustained"] = round(sus, 1)
         out["frac_of_sustained"] = round(ach / sus, 4)
     return out

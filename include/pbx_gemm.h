@@ -109,7 +109,7 @@ int pbx_set_split_k(pbx_handle_t h, int slices /* 0 = auto, 1 = never, >1 = forc
 int pbx_last_kernel(pbx_handle_t h);               /* pbx_kernel_t used by the last call */
 int pbx_last_split_k(pbx_handle_t h);              /* K slices used by the last call */
 int pbx_last_repack(pbx_handle_t h);               /* bit 0 / 1: A / B was re-laid out to a 16-byte-legal copy */
-int pbx_last_presplit(pbx_handle_t h);             /* 1: fp32 lo halves were pre-split in global memory (3xTF32) */
+int pbx_last_presplit(pbx_handle_t h);             /* fp32 mode of the last call: 0 in-kernel 3xTF32 split, 1 pre-split lo halves, 2 single tf32 (SB_ENABLE_JOINT_MATRIX=1) */
 int64_t pbx_launch_count(pbx_handle_t h);          /* kernels launched through this handle so far */
 int64_t pbx_workspace_bytes(pbx_handle_t h);       /* current size of the pooled workspace */
 

@@ -81,9 +81,14 @@ constexpr int ROW_BYTES = 128;  // one swizzle row
 // CG = 1: one CTA computes a 128 x BN tile.  CG = 2: a CTA pair (2-CTA cluster, cta_group::2)
 // computes a 256 x BN tile; each CTA stages its own 128 rows of A and BN/2 rows of B, so the
 // shared-memory read rate per SM halves for the same MMA rate.
-// PRE (fp32 only): the lo halves of both operands were computed by a pre-pass into global memory and arrive by
-// TMA like the raw tiles, so the CTA has no splitter warps and its shared memory carries no split traffic.
-template <int ES, int BN, int STAGES, int CG, int OS = 4, bool PRE = false>
+// PRE (fp32 only) selects how the 3xTF32 operands are produced:
+//   0  in-kernel split: splitter warps derive the lo tiles from the staged raw tiles
+//   1  pre-split: the lo halves of both operands were computed by a pre-pass into global memory and arrive by TMA
+//      like the raw tiles, so the CTA has no splitter warps and its shared memory carries no split traffic
+//   2  single tf32 product (no lo halves at all): the reduced-precision mode the reference reaches with
+//      SB_ENABLE_JOINT_MATRIX=1 (float storage, 10-bit-mantissa fragments, fp32 accumulate,
+//      src/interface/blas3/backend/nvidia_gpu.hpp:67-110); stages hold raw tiles only, so the ring is twice as deep
+template <int ES, int BN, int STAGES, int CG, int OS = 4, int PRE = 0>
 struct TcCfg {
   static constexpr bool TF32X3 = (ES == 4);
   static constexpr int BK = ROW_BYTES / ES;        // 64 (16-bit) or 32 (fp32) elements
@@ -93,7 +98,7 @@ struct TcCfg {
   static constexpr int A_BYTES = BM * ROW_BYTES;   // 16 KiB
   static constexpr int B_BYTES = BN_CTA * ROW_BYTES;
   static constexpr int RAW_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGE_BYTES = RAW_BYTES * (TF32X3 ? 2 : 1);  // + lo copies
+  static constexpr int STAGE_BYTES = RAW_BYTES * ((TF32X3 && PRE != 2) ? 2 : 1);  // + lo copies
   static constexpr int BAR_BYTES = 256;
   static constexpr int EPI_WARPS = 8;
   // 16-bit outputs: every epilogue warp owns two 32x32 staging tiles (column-major, rows contiguous)
@@ -105,8 +110,8 @@ struct TcCfg {
   static constexpr int ACC_STAGES = TF32X3 ? ((3 * BN <= 512) ? 2 : 1) : 2;
   static constexpr int RSUM_COL = ACC_STAGES * BN;
   static constexpr int TMEM_COLS = TF32X3 ? 512 : 2 * BN;
-  static constexpr int SPLIT_WARPS = (TF32X3 && !PRE) ? 4 : 0;
-  static constexpr int TMA_BYTES = RAW_BYTES * ((TF32X3 && PRE) ? 2 : 1);   // bytes one CTA's producer lands per stage
+  static constexpr int SPLIT_WARPS = (TF32X3 && PRE == 0) ? 4 : 0;
+  static constexpr int TMA_BYTES = RAW_BYTES * ((TF32X3 && PRE == 1) ? 2 : 1);   // bytes one CTA's producer lands per stage
   static constexpr int NUM_THREADS = 32 * (4 + EPI_WARPS + SPLIT_WARPS);
   static constexpr int NUM_SPLIT_THREADS = 32 * SPLIT_WARPS;
   static_assert(BN % (32 * 2) == 0 && BN <= 256 && (BN_CTA % 8) == 0, "tile width");
@@ -134,13 +139,13 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int64_t tile
 
 // M, N, ldc in TcParams are the KERNEL's view: with TRANS_OUT the caller passed (N, M) and the kernel's
 // D(row r, column c) is C(c, r), i.e. element address c + r*ldc instead of r + c*ldc.
-template <typename TIn, typename TOut, int BN, int STAGES, bool A_MN, bool B_MN, int CG, bool TRANS_OUT, bool PRE>
+template <typename TIn, typename TOut, int BN, int STAGES, bool A_MN, bool B_MN, int CG, bool TRANS_OUT, int PRE>
 __global__ void __launch_bounds__(TcCfg<sizeof(TIn), BN, STAGES, CG, sizeof(TOut), PRE>::NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmBlo, const TcParams p) {
   using Cfg = TcCfg<sizeof(TIn), BN, STAGES, CG, sizeof(TOut), PRE>;
-  static_assert(!PRE || Cfg::TF32X3, "pre-split operands exist for fp32 only");
+  static_assert(PRE == 0 || Cfg::TF32X3, "pre-split / single-tf32 modes exist for fp32 only");
   constexpr bool TF32X3 = Cfg::TF32X3;
   constexpr int BK = Cfg::BK;
   constexpr int ACC_STAGES = Cfg::ACC_STAGES;
@@ -169,7 +174,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (Cfg::EPI_BYTES > 0 && p.tma_store) tma_prefetch_desc(&tmC);
-    if (PRE) { tma_prefetch_desc(&tmAlo); tma_prefetch_desc(&tmBlo); }
+    if (PRE == 1) { tma_prefetch_desc(&tmAlo); tma_prefetch_desc(&tmBlo); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -199,7 +204,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       // pair mode without splitters (16-bit, pre-split fp32): both CTAs credit the leader's full barrier (the MMA
       // issuer waits there).  fp32 with in-kernel split: each CTA's splitter warps wait on their OWN full barrier.
-      constexpr bool kLeaderFull = (CG == 2) && (!TF32X3 || PRE);
+      constexpr bool kLeaderFull = (CG == 2) && (!TF32X3 || PRE != 0);
       for (int64_t tile = group; tile < p.total_tiles; tile += num_groups) {
         const TileCoord tc = decode_tile(p, tile);
         const int m0 = tc.mt * Cfg::TILE_M + (int)rank * BM;
@@ -230,7 +235,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             load(sB, &tmB, kb * BK, n0, zb);
           }
-          if (PRE) {   // lo tiles: same boxes of the pre-split copies, placed RAW_BYTES further
+          if (PRE == 1) {   // lo tiles: same boxes of the pre-split copies, placed RAW_BYTES further
             const uint32_t sAl = sA + Cfg::RAW_BYTES, sBl = sB + Cfg::RAW_BYTES;
             if (A_MN) {
 #pragma unroll
@@ -282,7 +287,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
           for (int kb = kc0; kb < kc1; ++kb) {
-            constexpr bool kSplit = TF32X3 && !PRE;
+            constexpr bool kSplit = TF32X3 && PRE == 0;
             const uint32_t ready = kSplit ? split_bar(stage) : full_bar(stage);
             // fp32 pair mode with in-kernel split: the peer's splitter warps wrote shared memory with ordinary stores
             if (CG == 2 && kSplit) mbar_wait_cluster(ready, phase); else mbar_wait(ready, phase);
@@ -294,7 +299,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint64_t adesc = make_smem_desc(sA + k * A_KSTEP, A_LBO, A_SBO, A_LT);
               const uint64_t bdesc = make_smem_desc(sB + k * B_KSTEP, B_LBO, B_SBO, B_LT);
               const uint32_t acc = (kb > kc0 || k > 0) ? 1u : 0u;
-              if (TF32X3) {
+              if (TF32X3 && PRE != 2) {
                 const uint64_t adesc_lo = make_smem_desc(sA + Cfg::RAW_BYTES + k * A_KSTEP, A_LBO, A_SBO, A_LT);
                 const uint64_t bdesc_lo = make_smem_desc(sB + Cfg::RAW_BYTES + k * B_KSTEP, B_LBO, B_SBO, B_LT);
                 mma(d_tmem, adesc_lo, bdesc, acc);
@@ -482,7 +487,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (OUT16 && tma_store && lane == 0) bulk_wait_read<0>();   // staging tiles must outlive their stores
     __syncwarp();
-  } else if (TF32X3 && !PRE && warp >= 4 + Cfg::EPI_WARPS) {
+  } else if (TF32X3 && PRE == 0 && warp >= 4 + Cfg::EPI_WARPS) {
     // ===================== fp32 -> (hi, lo) tf32 splitters (each CTA splits what it staged) ==============
     const int st = threadIdx.x - 32 * (4 + Cfg::EPI_WARPS);
     int stage = 0;
@@ -603,7 +608,7 @@ struct TcMaps {
   CUtensorMap a, b, c, alo, blo;
 };
 
-template <typename TIn, typename TOut, int BN, int STAGES, bool A_MN, bool B_MN, int CG, bool TRANS_OUT, bool PRE>
+template <typename TIn, typename TOut, int BN, int STAGES, bool A_MN, bool B_MN, int CG, bool TRANS_OUT, int PRE>
 int launch_inst(pbx_handle_t h, const TcMaps& tm, const TcParams& p) {
   using Cfg = TcCfg<sizeof(TIn), BN, STAGES, CG, sizeof(TOut), PRE>;
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -632,7 +637,7 @@ int launch_inst(pbx_handle_t h, const TcMaps& tm, const TcParams& p) {
   return PBX_OK;
 }
 
-template <typename TIn, typename TOut, int BN, int STAGES, int CG, bool TRANS_OUT, bool PRE>
+template <typename TIn, typename TOut, int BN, int STAGES, int CG, bool TRANS_OUT, int PRE>
 int launch_major(pbx_handle_t h, bool a_mn, bool b_mn, const TcMaps& tm, const TcParams& p) {
   if (a_mn) {
     return b_mn ? launch_inst<TIn, TOut, BN, STAGES, true, true, CG, TRANS_OUT, PRE>(h, tm, p)
@@ -644,9 +649,10 @@ int launch_major(pbx_handle_t h, bool a_mn, bool b_mn, const TcMaps& tm, const T
 
 // tile configurations, most efficient first: CTA pair 256x256, CTA pair 256x128, single CTA 128x128;
 // bn == 64 is the skinny-M configuration (operands swapped, 128 columns of C x 64 rows per tile)
-template <typename TIn, typename TOut, bool PRE>
+template <typename TIn, typename TOut, int PRE>
 int launch_cfg_pre(pbx_handle_t h, int cg, int bn, bool a_mn, bool b_mn, const TcMaps& tm, const TcParams& p) {
-  constexpr bool F32 = sizeof(TIn) == 4;
+  // fp32 stages hold raw + lo tiles (half as many stages as 16-bit) unless there are no lo tiles at all (PRE == 2)
+  constexpr bool F32 = sizeof(TIn) == 4 && PRE != 2;
   if (bn == 64) return launch_major<TIn, TOut, 64, F32 ? 4 : 8, 1, true, PRE>(h, a_mn, b_mn, tm, p);  // swapped operands
   if (cg == 2 && bn == 256) return launch_major<TIn, TOut, 256, F32 ? 3 : 6, 2, false, PRE>(h, a_mn, b_mn, tm, p);
   if (cg == 2) return launch_major<TIn, TOut, 128, F32 ? 4 : 8, 2, false, PRE>(h, a_mn, b_mn, tm, p);
@@ -654,11 +660,12 @@ int launch_cfg_pre(pbx_handle_t h, int cg, int bn, bool a_mn, bool b_mn, const T
 }
 
 template <typename TIn, typename TOut>
-int launch_cfg(pbx_handle_t h, int cg, int bn, bool a_mn, bool b_mn, bool pre, const TcMaps& tm, const TcParams& p) {
+int launch_cfg(pbx_handle_t h, int cg, int bn, bool a_mn, bool b_mn, int pre, const TcMaps& tm, const TcParams& p) {
   if constexpr (sizeof(TIn) == 4) {
-    if (pre) return launch_cfg_pre<TIn, TOut, true>(h, cg, bn, a_mn, b_mn, tm, p);
+    if (pre == 1) return launch_cfg_pre<TIn, TOut, 1>(h, cg, bn, a_mn, b_mn, tm, p);
+    if (pre == 2) return launch_cfg_pre<TIn, TOut, 2>(h, cg, bn, a_mn, b_mn, tm, p);
   }
-  return launch_cfg_pre<TIn, TOut, false>(h, cg, bn, a_mn, b_mn, tm, p);
+  return launch_cfg_pre<TIn, TOut, 0>(h, cg, bn, a_mn, b_mn, tm, p);
 }
 
 struct TcPlan {
@@ -772,7 +779,11 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
   // shapes (arithmetic intensity < 256 flop/B) keep the in-kernel split: the pre-pass would triple their traffic.
   bool pre = false;
   const void* lo_ptr[2] = {nullptr, nullptr};
-  if (f32) {
+  // SB_ENABLE_JOINT_MATRIX=1 is the reference's switch (read per call, nvidia_gpu.hpp:68-69) from the fp32 kernels to
+  // its tensor-core kernels with reduced-precision fragments; here it selects the single-tf32 product.
+  const char* jm_env = getenv("SB_ENABLE_JOINT_MATRIX");
+  const bool tf32x1 = f32 && jm_env != nullptr && jm_env[0] == '1';
+  if (f32 && !tf32x1) {
     const int pre_env = getenv("PBX_TF32_PRESPLIT") ? atoi(getenv("PBX_TF32_PRESPLIT")) : -1;
     const double flops = 2.0 * (double)c.m * (double)c.n * (double)c.k * (double)c.batch;
     const double byts = 4.0 * ((double)c.m * c.k + (double)c.k * c.n + (double)c.m * c.n) * (double)c.batch;
@@ -805,7 +816,7 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
     h->last_error = "cuTensorMapEncodeTiled failed";
     return PBX_ERR_CUDA;
   }
-  h->last_presplit = pre ? 1 : 0;
+  h->last_presplit = tf32x1 ? 2 : (pre ? 1 : 0);
   TcParams p;
   p.C = c.C; p.ws = (float*)h->ws;
   p.M = X.mn; p.N = Y.mn; p.K = c.k; p.ldc = c.ldc; p.sc = c.sc;
@@ -841,11 +852,11 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
   }
 
   switch (c.dtype) {
-    case PBX_F32: return launch_cfg<float, float>(h, cg, bn, a_mn, b_mn, pre, tm, p);
-    case PBX_F16: return launch_cfg<__half, __half>(h, cg, bn, a_mn, b_mn, pre, tm, p);
-    case PBX_F16_F32: return launch_cfg<__half, float>(h, cg, bn, a_mn, b_mn, pre, tm, p);
-    case PBX_BF16: return launch_cfg<__nv_bfloat16, __nv_bfloat16>(h, cg, bn, a_mn, b_mn, pre, tm, p);
-    case PBX_BF16_F32: return launch_cfg<__nv_bfloat16, float>(h, cg, bn, a_mn, b_mn, pre, tm, p);
+    case PBX_F32: return launch_cfg<float, float>(h, cg, bn, a_mn, b_mn, tf32x1 ? 2 : (pre ? 1 : 0), tm, p);
+    case PBX_F16: return launch_cfg<__half, __half>(h, cg, bn, a_mn, b_mn, tf32x1 ? 2 : (pre ? 1 : 0), tm, p);
+    case PBX_F16_F32: return launch_cfg<__half, float>(h, cg, bn, a_mn, b_mn, tf32x1 ? 2 : (pre ? 1 : 0), tm, p);
+    case PBX_BF16: return launch_cfg<__nv_bfloat16, __nv_bfloat16>(h, cg, bn, a_mn, b_mn, tf32x1 ? 2 : (pre ? 1 : 0), tm, p);
+    case PBX_BF16_F32: return launch_cfg<__nv_bfloat16, float>(h, cg, bn, a_mn, b_mn, tf32x1 ? 2 : (pre ? 1 : 0), tm, p);
   }
   return PBX_ERR_INVALID_ARG;
 }

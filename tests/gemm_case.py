@@ -54,12 +54,15 @@ class Case:
     kernel: int = 0                # forced pbx_kernel_t (0 = auto)
     split_k: int = 0
     env: tuple = ()                # ((name, value), ...) set around the call (PBX_TC_CONFIG, PBX_TF32_RAW_HI ...)
+    zero_low_bits: int = 0         # clear the low mantissa bits of the fp32 inputs (reference set_to_zero_last_nbits,
+                                   # test/blas_test.hpp:225-244: 13 for tf32 / half fragments)
 
     def ident(self) -> str:
         return (f"{self.dtype}-{self.api}-{self.transa}{self.transb}-{self.m}x{self.n}x{self.k}-a{self.alpha}"
                 f"b{self.beta}-ld{self.lda_mul}{self.ldb_mul}{self.ldc_mul}-off{self.offset}-bs{self.batch}"
                 f"t{self.batch_type}-s{self.stride_a_mul}{self.stride_b_mul}{self.stride_c_mul}"
-                f"-k{self.kernel}-sk{self.split_k}" + "".join(f"-{name[4:]}={val}" for name, val in self.env))
+                f"-k{self.kernel}-sk{self.split_k}" + "".join(f"-{name[4:]}={val}" for name, val in self.env)
+                + (f"-z{self.zero_low_bits}" if self.zero_low_bits else ""))
 
 
 @dataclasses.dataclass
@@ -111,6 +114,10 @@ def run_case(handle: blas.SB_Handle, cs: Case) -> Result:
     a_h = _storage_round(oracle.random_uniform(rng, buf_a, npdt), cs.dtype)
     b_h = _storage_round(oracle.random_uniform(rng, buf_b, npdt), cs.dtype)
     c_h = _out_round(oracle.random_uniform(rng, buf_c, npdt), cs.dtype)
+    if cs.zero_low_bits and npdt == np.float32:
+        mask = np.uint32((0xFFFFFFFF << cs.zero_low_bits) & 0xFFFFFFFF)
+        for arr in (a_h, b_h, c_h):
+            arr.view(np.uint32)[...] &= mask
     off = cs.offset
 
     # ---- expected (strided layout, per batch entry), as the reference's tests do ----

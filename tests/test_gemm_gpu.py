@@ -262,6 +262,35 @@ def test_joint_matrix_grid(handle, dt):
     _run_all(handle, cases)
 
 
+def test_joint_matrix_tf32_mode(handle):
+    """SB_ENABLE_JOINT_MATRIX=1 (the reference's per-call switch, nvidia_gpu.hpp:68-69) runs float GEMMs with
+    10-bit-mantissa fragments and fp32 accumulation; here: one tf32 MMA per product.  As in
+    test/unittest/joint_matrix/tf32_float_16_16_8.cpp the inputs carry 13 zeroed mantissa bits, so the narrow
+    fragments are exact and the float tolerances apply.  Without the switch the same call is a 3xTF32 GEMM."""
+    env = (("SB_ENABLE_JOINT_MATRIX", "1"),)
+    cases = []
+    for m, n, k in [(11, 11, 17), (33, 63, 64), (65, 127, 65), (255, 511, 127), (1024, 1535, 1536)]:
+        for (ta, tb), be in itertools.product(TRANS, [0.0, 1.5]):
+            cases.append(Case(dtype="f32", transa=ta, transb=tb, m=m, n=n, k=k, alpha=1.5, beta=be, offset=32,
+                              kernel=TCGEN05, env=env, zero_low_bits=13))
+    for cfg in ("1,128", "2,128", "2,256"):
+        cases.append(Case(dtype="f32", transa="t", m=520, n=392, k=1096, alpha=1.5, beta=0.5, kernel=TCGEN05,
+                          env=env + (("PBX_TC_CONFIG", cfg),), zero_low_bits=13))
+        cases.append(Case(dtype="f32", api="strided", m=264, n=392, k=200, alpha=1.0, beta=0.0, batch=5,
+                          kernel=TCGEN05, env=env + (("PBX_TC_CONFIG", cfg),), zero_low_bits=13))
+    cases.append(Case(dtype="f32", m=40, n=1000, k=520, alpha=1.5, beta=0.5, kernel=TCGEN05, env=env, zero_low_bits=13))
+    cases.append(Case(dtype="f32", m=300, n=260, k=4104, alpha=1.0, beta=0.5, kernel=TCGEN05, split_k=3, env=env,
+                      zero_low_bits=13))
+    _run_all(handle, cases)
+    run_case(handle, cases[0])
+    assert handle.last_presplit == 2
+    # general inputs: the single-tf32 product is only tf32-accurate, and the default path must not be affected
+    r = run_case(handle, Case(dtype="f32", m=256, n=256, k=512, alpha=1.0, beta=0.0, kernel=TCGEN05, env=env))
+    assert not r.ok and r.max_rel_bound < 2e-3, r          # ~2^-11 relative to |A||B|, beyond the fp32 bar
+    r = run_case(handle, Case(dtype="f32", m=256, n=256, k=512, alpha=1.0, beta=0.0, kernel=TCGEN05))
+    assert r.ok and handle.last_presplit != 2, r
+
+
 # ---- committed golden vectors (tests/golden/make_golden.py) through the CUDA path ----------------------
 def test_golden_fixtures_gpu(handle):
     from pathlib import Path
