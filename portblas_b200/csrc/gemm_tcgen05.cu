@@ -712,6 +712,15 @@ TcPlan make_plan(pbx_handle_t h, const PbxGemmCall& c) {
       }
     }
   }
+  // HBM-bound 16-bit shapes (BASELINE cfg4: 4096 x 256^3, 85 flop/B): measured on B200, 148 independent 128x128
+  // tiles keep DRAM busier than 74 CTA pairs on 256x256 tiles (529 vs 518 TFLOP/s) -- the tensor pipe is a third
+  // loaded either way, what counts is how many independent load streams are in flight.
+  if (!(force && fcg) && !plan.swap && pbx_in_size(c.dtype) == 2) {
+    const double flops = 2.0 * (double)c.m * (double)c.n * (double)c.k;
+    const double byts = 2.0 * ((double)c.m * c.k + (double)c.k * c.n) + (double)pbx_out_size(c.dtype) * c.m * c.n;
+    const Cand small = {1, 128};
+    if (flops / byts < 100.0 && tiles_of(small) >= 2 * (int64_t)h->sm_count) { plan.cg = 1; plan.bn = 128; }
+  }
   // K slices.  The reference splits by depth = ceil(4*CUs / tiles) when K > 2048
   // (gemm_partial_local.hpp:191-199, portblas_handle.hpp:323).  Here: when the output tiles cannot fill
   // half of the SM (pairs), spread the K loop over up to two waves of them, but keep at least 4 K blocks

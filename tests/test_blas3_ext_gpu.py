@@ -138,3 +138,31 @@ def test_cgemm_conj_quirk_batches_and_errors(handle, dt):
               CgemmCase(dtype=dt, transa="x"), CgemmCase(dtype=dt, transb="x"),
               CgemmCase(dtype=dt, m=0), CgemmCase(dtype=dt, k=0)]
     _run_all(handle, run_cgemm, cases)
+
+
+@pytest.mark.parametrize("dt_name", ["f16", "bf16"])
+def test_symm_16bit_storage(handle, dt_name):
+    """16-bit storage: the mirror pass is type-agnostic (2-byte elements) and the product runs on tcgen05 kind::f16;
+    checked on the device against the fp64 product of the mirrored matrix (bars of the 16-bit GEMM tests)."""
+    import torch
+    from portblas_b200 import blas
+    dt, tol = (torch.float16, 2e-3) if dt_name == "f16" else (torch.bfloat16, 1.6e-2)
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    for side, uplo, m, n in [("l", "u", 264, 200), ("r", "l", 136, 392), ("l", "l", 63, 17)]:
+        kk = m if side == "l" else n
+        lda, ldb, ldc = kk + 8, m, m + 8
+        a = (torch.rand(lda * kk, device="cuda", generator=gen) * 7 - 2).to(dt)
+        b = (torch.rand(ldb * n, device="cuda", generator=gen) * 7 - 2).to(dt)
+        c0 = (torch.rand(ldc * n, device="cuda", generator=gen) * 7 - 2).to(dt)
+        c = c0.clone()
+        blas._symm(handle, side, uplo, m, n, 1.5, a, lda, b, ldb, 0.5, c, ldc)
+        handle.wait()
+        f64 = torch.float64
+        A = a.view(kk, lda).T[:kk].to(f64)
+        tri = torch.tril(A) if uplo == "l" else torch.triu(A)
+        S = tri + tri.T - torch.diag(torch.diag(A))
+        B, C0, C = b.view(n, ldb).T[:m].to(f64), c0.view(n, ldc).T.to(f64), c.view(n, ldc).T.to(f64)
+        want = 1.5 * (S @ B if side == "l" else B @ S) + 0.5 * C0[:m]
+        bound = 1.5 * (S.abs() @ B.abs() if side == "l" else B.abs() @ S.abs()) + 0.5 * C0[:m].abs()
+        assert float(((C[:m] - want).abs() / bound).max()) <= tol
+        assert torch.equal(C[m:], C0[m:])      # ld padding untouched
