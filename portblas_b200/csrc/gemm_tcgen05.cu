@@ -65,14 +65,23 @@ template <typename T> struct OutCvt;
 template <> struct OutCvt<float> {
   __device__ static float load(const float* p) { return *p; }
   __device__ static void store(float* p, float v) { *p = v; }
+  __device__ static uint32_t pack2(float lo, float) { return __float_as_uint(lo); }   // unused for 32-bit outputs
 };
 template <> struct OutCvt<__half> {
   __device__ static float load(const __half* p) { return __half2float(*p); }
   __device__ static void store(__half* p, float v) { *p = __float2half_rn(v); }
+  __device__ static uint32_t pack2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
 };
 template <> struct OutCvt<__nv_bfloat16> {
   __device__ static float load(const __nv_bfloat16* p) { return __bfloat162float(*p); }
   __device__ static void store(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+  __device__ static uint32_t pack2(float lo, float hi) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
 };
 
 constexpr int BM = 128;         // rows of D held by one CTA (TMEM lanes)
@@ -438,9 +447,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ++store_blk;
             if (lane == 0) bulk_wait_read<1>();   // the store that last used this buffer has read it
             __syncwarp();
-            TOut* st = stage_ptr + buf * (Cfg::EPI_TILE_BYTES / (int)sizeof(TOut)) + lane;
+            // Two-byte stores put two lanes on every bank word (ncu: 40 % of the shared-memory wavefronts of a short-K
+            // bf16 GEMM were conflicts).  Lanes 2p / 2p+1 swap one value per column pair instead, so the even lane
+            // writes the packed word {row 2p, row 2p+1} of column j and the odd lane that of column j+1: 16
+            // conflict-free 32-bit stores per lane instead of 32 two-byte ones.
+            uint32_t* stw = reinterpret_cast<uint32_t*>(stage_ptr + buf * (Cfg::EPI_TILE_BYTES / (int)sizeof(TOut)));
+            const int pr = lane >> 1;
+            const bool odd = (lane & 1) != 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) OutCvt<TOut>::store(st + j * 32, p.alpha * __uint_as_float(v[j]));
+            for (int j = 0; j < 32; j += 2) {
+              const float e = p.alpha * __uint_as_float(v[j]), o = p.alpha * __uint_as_float(v[j + 1]);
+              const float recv = __shfl_xor_sync(0xffffffffu, odd ? e : o, 1);
+              stw[(j + (odd ? 1 : 0)) * 16 + pr] = OutCvt<TOut>::pack2(odd ? recv : e, odd ? o : recv);
+            }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
