@@ -10,7 +10,9 @@ include/sb_handle/portblas_handle.h:51-60); sharding is new in this build (SURVE
 
 Both partitions are embarrassingly parallel.  The only collective is the optional gather of C
 into one buffer (``gather_c_mblocks`` / ``gather_c_batches``), NCCL all_gather over NVLink on
-GPUs (gloo on CPU in the tests).
+GPUs (gloo on CPU in the tests).  ``gemm_mblock_gather_overlapped`` hides that gather behind the
+compute: the local row block is produced in column panels and panel j travels over NVLink (on a
+side stream) while panel j+1 is still on the tensor cores.
 """
 from __future__ import annotations
 
@@ -105,3 +107,48 @@ def gather_c_batches(c_local: torch.Tensor, per_matrix: int, batch: int, world: 
     out = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(out, pad, group=group)
     return torch.cat([out[r][:shapes[r][1] * per_matrix] for r in range(world)])
+
+
+def panel_ranges(n: int, panels: int, align: int = 256) -> List[Tuple[int, int]]:
+    """[(n0, nb)] column panels of about n/panels columns, multiples of ``align`` except the last."""
+    per = max(align, ((n + panels - 1) // panels + align - 1) // align * align)
+    return [(n0, min(per, n - n0)) for n0 in range(0, n, per)]
+
+
+def gemm_mblock_gather_overlapped(gemm_panel, m: int, n: int, rows: int, world: int, dtype, device, panels: int = 8,
+                                  group=None, side_stream=None) -> torch.Tensor:
+    """M-block sharded GEMM whose C gather overlaps the compute.
+
+    ``gemm_panel(n0, nb, c_panel)`` must compute columns [n0, n0+nb) of this rank's ``rows`` x n row block into the
+    compact column-major tensor ``c_panel`` (rows*nb elements, ld == rows) -- on the GPU an ordinary ``blas._gemm`` on
+    the handle's stream.  Every rank owns the same number of rows (m == rows*world).  After panel j is enqueued its
+    all-gather is issued on ``side_stream`` (ordered after the panel's GEMM by an event), so the NVLink transfer of
+    panel j runs under the GEMM of panel j+1; the gathered panels land directly in their final place of the full
+    compact m x n matrix, which is returned on every rank."""
+    if rows * world != m:
+        raise ValueError("gemm_mblock_gather_overlapped needs equal row blocks (m == rows * world)")
+    cuda = torch.device(device).type == "cuda"
+    c_loc = torch.empty(rows * n, dtype=dtype, device=device)
+    full = torch.empty(m * n, dtype=dtype, device=device)
+    stages = []
+    main = torch.cuda.current_stream(device) if cuda else None
+    if cuda and side_stream is None:
+        side_stream = torch.cuda.Stream(device=device)
+    for n0, nb in panel_ranges(n, panels):
+        c_panel = c_loc[n0 * rows:(n0 + nb) * rows]
+        gemm_panel(n0, nb, c_panel)
+        stage = torch.empty(world * nb * rows, dtype=dtype, device=device)   # [world][nb][rows]
+        stages.append(stage)
+        if cuda:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side_stream.wait_event(ev)
+            with torch.cuda.stream(side_stream):
+                dist.all_gather_into_tensor(stage, c_panel, group=group)
+                full.view(n, world, rows)[n0:n0 + nb].copy_(stage.view(world, nb, rows).permute(1, 0, 2))
+        else:
+            dist.all_gather_into_tensor(stage, c_panel, group=group)
+            full.view(n, world, rows)[n0:n0 + nb].copy_(stage.view(world, nb, rows).permute(1, 0, 2))
+    if cuda:
+        main.wait_stream(side_stream)
+    return full

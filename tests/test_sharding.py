@@ -71,6 +71,20 @@ def _worker(rank, world, port, q):
                 opa_full = np.lib.stride_tricks.as_strided(A, (k, m), (8, lda * 8)).T
             want = (opa_full @ B.reshape(n, k).T).T.reshape(-1)
             assert np.allclose(full, want, rtol=1e-12, atol=1e-12)
+        # panel-overlapped gather: numpy stands in for the device GEMM of each column panel
+        m2, n2, k2 = 64 * world, 1000, 37
+        A2, B2 = rng.uniform(-2, 5, m2 * k2), rng.uniform(-2, 5, k2 * n2)
+        rows2 = m2 // world
+        opa2 = A2.reshape(k2, m2).T[rank * rows2:(rank + 1) * rows2]
+        opb2 = B2.reshape(n2, k2).T
+
+        def gemm_panel(n0, nb, c_panel):
+            c_panel.copy_(torch.from_numpy((opa2 @ opb2[:, n0:n0 + nb]).T.copy().reshape(-1)))
+        full2 = sharding.gemm_mblock_gather_overlapped(gemm_panel, m2, n2, rows2, world, torch.float64, "cpu",
+                                                       panels=3).numpy()
+        want2 = (A2.reshape(k2, m2).T @ opb2).T.reshape(-1)
+        assert np.allclose(full2, want2, rtol=1e-12, atol=1e-12)
+        assert sharding.panel_ranges(1000, 3) == [(0, 512), (512, 488)]
         # batch sharding
         batch, per = 7, 12
         Cb = rng.uniform(-2, 5, batch * per)
