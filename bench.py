@@ -370,6 +370,33 @@ def main():
             to = torch.tensor([g0.elapsed_time(g1)], device=dev, dtype=torch.float64)
             dist.all_reduce(to, op=dist.ReduceOp.MAX)
             overlap_ms = float(to.item())
+            # fused form: the epilogue of this rank's M-block stores every tile into ALL ranks' C (CUDA IPC peer
+            # pointers), no staging buffer and no collective
+            c_full = torch.zeros(m * n, device=dev, dtype=tdt)
+            ptrs = sharding.share_full_c(h, c_full)
+            for it in range(2):
+                torch.cuda.synchronize()
+                dist.barrier()
+                g0.record()
+                sharding.gemm_mblock_fused_gather(h, w["ta"], w["tb"], m, n, k, w["alpha"], a_v, lda, b, ldb, 0.0, ptrs, m,
+                                                  tdt, world, rank, align=256)
+                g1.record()
+                torch.cuda.synchronize()
+            dist.barrier()
+            tf_ = torch.tensor([g0.elapsed_time(g1)], device=dev, dtype=torch.float64)
+            dist.all_reduce(tf_, op=dist.ReduceOp.MAX)
+            fused_ms = float(tf_.item())
+            # every rank must now hold the SAME full C (bitwise: compare checksums across ranks), and this rank's rows
+            # must equal its own plain GEMM
+            cs = torch.tensor([float(c_full.double().sum()), float(c_full.double().abs().sum())], device=dev,
+                              dtype=torch.float64)
+            all_cs = [torch.empty_like(cs) for _ in range(world)]
+            dist.all_gather(all_cs, cs)
+            same = all(bool(torch.equal(all_cs[0], x)) for x in all_cs)
+            mine = c_full.view(n, m)[:, c_off:c_off + m_loc]
+            local_ok = bool(torch.equal(mine, c.view(n, ldc)[:, c_off:c_off + m_loc]))
+            fused_ok = same and local_ok
+            del c_full
 
     # ---- end-to-end: HOST (pinned) buffers through the public host-buffer call, H2D + D2H in the timed region ----
     e2e = None
@@ -430,6 +457,8 @@ def main():
             line["gather_c_ms"] = round(gather_ms, 3)
             if overlap_ms is not None:
                 line["gemm_plus_overlapped_gather_ms"] = round(overlap_ms, 3)
+                line["gemm_fused_gather_ms"] = round(fused_ms, 3)
+                line["gemm_fused_gather_ok"] = fused_ok
         print(json.dumps(line), flush=True)
     h.close()
     if world > 1:

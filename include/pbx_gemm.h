@@ -203,6 +203,18 @@ int pbx_zgemm(pbx_handle_t h, char transa, char transb, int64_t m, int64_t n, in
               const double* beta, void* C, int64_t ldc, int64_t stridec, int64_t batch);
 int pbx_set_conj_transpose(pbx_handle_t h, int enable);
 
+/* ---- multi-GPU: the C gather fused into the GEMM's stores ---------------------------------------------------
+ * One process per GPU.  A rank exports its full C with pbx_ipc_export (64-byte CUDA IPC handle
+ * of the underlying allocation + byte offset), the peers map it with pbx_ipc_import, and every rank then runs its
+ * M-block with pbx_gemm_multicast: C_list[0] is the local copy (read when beta != 0), C_list[1..n_dst-1] the same
+ * row block inside the peers' C.  The tensor-core epilogue stores each finished tile to all copies over NVLink
+ * while the next tile is computed; no staging buffer, no collective call.  batch == 1, n_dst <= 8.               */
+int pbx_gemm_multicast(pbx_handle_t h, int dtype, char transa, char transb, int64_t m, int64_t n, int64_t k,
+                       const void* alpha, const void* A, int64_t lda, const void* B, int64_t ldb, const void* beta,
+                       void* const* C_list, int n_dst, int64_t ldc);
+int pbx_ipc_export(pbx_handle_t h, const void* dptr, void* handle_out /* 64 bytes */, int64_t* offset_out);
+int pbx_ipc_import(pbx_handle_t h, const void* handle /* 64 bytes */, int64_t offset, void** dptr_out);
+
 /* ---- host-buffer convenience path (used for the end-to-end metric) -------
  * Same semantics as pbx_gemm, but A, B, C are HOST pointers (ideally pinned):
  * stages H2D on the handle's stream, runs the GEMM, copies C back and

@@ -56,6 +56,10 @@ SYMBOLS = {
     "pbx_zgemm": (c_int, [c_void_p, c_char, c_char, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64,
                           c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64]),
     "pbx_set_conj_transpose": (c_int, [c_void_p, c_int]),
+    "pbx_gemm_multicast": (c_int, [c_void_p, c_int, c_char, c_char, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64,
+                                   c_void_p, c_int64, c_void_p, POINTER(c_void_p), c_int, c_int64]),
+    "pbx_ipc_export": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int64)]),
+    "pbx_ipc_import": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_void_p)]),
     "pbx_gemm_host": (c_int, [c_void_p, c_int, c_char, c_char] + _GEMM_TAIL),
     "pbx_malloc": (c_int, [c_void_p, POINTER(c_void_p), c_int64]),
     "pbx_free": (c_int, [c_void_p, c_void_p]),

@@ -254,3 +254,36 @@ def gemm_host(sb_handle: SB_Handle, transa, transb, m, n, k, alpha, a_host: torc
         ctypes.cast(ctypes.pointer(be), ctypes.c_void_p), ctypes.c_void_p(c_host.data_ptr()), int(ldc), int(stridec),
         int(batch_size), int(batch_type))
     _check(sb_handle, st)
+
+
+# ---- multi-GPU: the gather of C fused into the GEMM's stores (include/pbx_gemm.h: pbx_gemm_multicast) --------------
+def ipc_export(sb_handle: SB_Handle, t: torch.Tensor):
+    """(64-byte CUDA IPC handle, byte offset) of the allocation behind a CUDA tensor -- picklable, for the peers."""
+    hbuf = ctypes.create_string_buffer(64)
+    off = ctypes.c_int64(0)
+    _check(sb_handle, sb_handle._lib.pbx_ipc_export(sb_handle._h, ctypes.c_void_p(t.data_ptr()), hbuf, ctypes.byref(off)))
+    return bytes(hbuf.raw), int(off.value)
+
+
+def ipc_import(sb_handle: SB_Handle, exported) -> int:
+    """Device pointer (int) in THIS process for a peer's exported tensor."""
+    hbytes, off = exported
+    hbuf = ctypes.create_string_buffer(hbytes, 64)
+    out = ctypes.c_void_p()
+    _check(sb_handle, sb_handle._lib.pbx_ipc_import(sb_handle._h, hbuf, ctypes.c_int64(off), ctypes.byref(out)))
+    return int(out.value)
+
+
+def _gemm_multicast(sb_handle: SB_Handle, _TransA, _TransB, _M, _N, _K, _alpha, a_, _lda, b_, _ldb, _beta, c_ptrs,
+                    _ldc, c_dtype: torch.dtype) -> None:
+    """``_gemm`` whose result is written to every pointer of ``c_ptrs`` (ints; [0] = this GPU's C, the rest are peer
+    copies from ``ipc_import``), all with leading dimension ``_ldc``."""
+    dt = _DTYPES[(a_.dtype, c_dtype)]
+    al, be = _scalar(dt, float(_alpha)), _scalar(dt, float(_beta))
+    arr = (ctypes.c_void_p * len(c_ptrs))(*[ctypes.c_void_p(int(p)) for p in c_ptrs])
+    st = sb_handle._lib.pbx_gemm_multicast(
+        sb_handle._h, dt, str(_TransA).encode()[:1], str(_TransB).encode()[:1], int(_M), int(_N), int(_K),
+        ctypes.cast(ctypes.pointer(al), ctypes.c_void_p), ctypes.c_void_p(a_.data_ptr()), int(_lda),
+        ctypes.c_void_p(b_.data_ptr()), int(_ldb), ctypes.cast(ctypes.pointer(be), ctypes.c_void_p), arr, len(c_ptrs),
+        int(_ldc))
+    _check(sb_handle, st)

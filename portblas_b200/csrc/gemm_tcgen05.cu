@@ -58,6 +58,8 @@ struct TcParams {
   int a_batched, b_batched;
   int tma_store;     // 16-bit C through shared memory + TMA store (needs beta == 0, aligned C, no split-K)
   int c_vec;         // TRANS_OUT: C rows of 32 elements may be stored as 16-byte vectors
+  int n_extra;       // multicast GEMM: the epilogue also stores the tile into these copies of C (peer GPUs' memory,
+  void* Cx[7];       // mapped through CUDA IPC; same ldc / batch stride as C) -- the gather rides on the GEMM's stores
   int64_t total_tiles;
 };
 
@@ -467,11 +469,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               bulk_commit();
             }
           } else {
-            TOut* dst = reinterpret_cast<TOut*>(p.C) + (int64_t)tc.b * p.sc + m + (n0 + c0) * p.ldc;
+            const int64_t c_off = (int64_t)tc.b * p.sc + m + (n0 + c0) * p.ldc;
+            TOut* dst = reinterpret_cast<TOut*>(p.C) + c_off;
             if (full) {
               if (beta0) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) OutCvt<TOut>::store(dst + j * p.ldc, p.alpha * __uint_as_float(v[j]));
+                for (int j = 0; j < 32; ++j) {
+                  const float r = p.alpha * __uint_as_float(v[j]);
+                  v[j] = __float_as_uint(r);
+                  OutCvt<TOut>::store(dst + j * p.ldc, r);
+                }
               } else {
 #pragma unroll
                 for (int j0 = 0; j0 < 32; j0 += 8) {   // 8 loads in flight, then 8 stores
@@ -479,10 +486,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                   for (int j = 0; j < 8; ++j) cin[j] = OutCvt<TOut>::load(dst + (j0 + j) * p.ldc);
 #pragma unroll
-                  for (int j = 0; j < 8; ++j)
-                    OutCvt<TOut>::store(dst + (j0 + j) * p.ldc,
-                                        p.alpha * __uint_as_float(v[j0 + j]) + p.beta * cin[j]);
+                  for (int j = 0; j < 8; ++j) {
+                    const float r = p.alpha * __uint_as_float(v[j0 + j]) + p.beta * cin[j];
+                    v[j0 + j] = __float_as_uint(r);
+                    OutCvt<TOut>::store(dst + (j0 + j) * p.ldc, r);
+                  }
                 }
+              }
+              // multicast: the same 32 x 32 block goes to every other copy of C (peer memory over NVLink); the stores
+              // are posted, so the transfer of this tile overlaps the mainloop of the next one
+              for (int x = 0; x < p.n_extra; ++x) {
+                TOut* dx = reinterpret_cast<TOut*>(p.Cx[x]) + c_off;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) OutCvt<TOut>::store(dx + j * p.ldc, __uint_as_float(v[j]));
               }
             } else {
 #pragma unroll
@@ -491,6 +507,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   float r = p.alpha * __uint_as_float(v[j]);
                   if (!beta0) r += p.beta * OutCvt<TOut>::load(dst + j * p.ldc);
                   OutCvt<TOut>::store(dst + j * p.ldc, r);
+                  for (int x = 0; x < p.n_extra; ++x)
+                    OutCvt<TOut>::store(reinterpret_cast<TOut*>(p.Cx[x]) + c_off + j * p.ldc, r);
                 }
               }
             }
@@ -706,7 +724,7 @@ TcPlan make_plan(pbx_handle_t h, const PbxGemmCall& c) {
   auto usable = [&](const Cand& cd) { return !(cd.cg == 2 && c.m <= 128) && !(cd.bn == 256 && c.n <= 128); };
   TcPlan plan = {1, 128, 1, false};
   const char* swap_env = getenv("PBX_TC_SWAP");   // "0" disables the skinny-M operand swap (testing)
-  const bool want_swap = c.m <= 64 && c.n > c.m && !(swap_env && atoi(swap_env) == 0);
+  const bool want_swap = c.m <= 64 && c.n > c.m && !(swap_env && atoi(swap_env) == 0) && c.n_extra == 0;
   const char* force = getenv("PBX_TC_CONFIG");  // "cg,bn" (testing)
   int fcg = 0, fbn = 0;
   if (force && sscanf(force, "%d,%d", &fcg, &fbn) == 2 && (fcg == 1 || fcg == 2) && (fbn == 128 || (fbn == 256 && fcg == 2))) {
@@ -748,7 +766,8 @@ TcPlan make_plan(pbx_handle_t h, const PbxGemmCall& c) {
   const Cand chosen = {plan.cg, plan.bn};
   const int64_t tiles = plan.swap ? ((c.n + 127) / 128) * c.batch : tiles_of(chosen), units = h->sm_count / plan.cg;
   int64_t slices = 1;
-  if (h->forced_split_k > 1) slices = h->forced_split_k;
+  if (c.n_extra > 0) slices = 1;   // multicast epilogue: the tile is stored straight from TMEM, no split-K partials
+  else if (h->forced_split_k > 1) slices = h->forced_split_k;
   else if (h->forced_split_k == 0 && tiles * 2 <= units && kb >= 16) {
     slices = (2 * units) / tiles;
     if (slices > kb / 4) slices = kb / 4;
@@ -867,13 +886,15 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
   const int64_t eo = (int64_t)pbx_out_size(c.dtype);
   p.c_vec = (((uintptr_t)c.C % 16 == 0) && (c.ldc * eo) % 16 == 0 && (c.sc * eo) % 16 == 0) ? 1 : 0;
   p.total_tiles = (int64_t)p.m_tiles * p.n_tiles * c.batch * slices;
+  p.n_extra = c.n_extra;
+  for (int x = 0; x < 7; ++x) p.Cx[x] = x < c.n_extra ? c.c_extra[x] : nullptr;
 
   // 16-bit C with beta == 0 leaves through shared memory + TMA stores when C is TMA-legal
   tm.c = tm.a;  // placeholder when unused (never dereferenced)
   p.tma_store = 0;
   const bool out16 = (c.dtype == PBX_F16 || c.dtype == PBX_BF16);
   const char* ts_env = getenv("PBX_TMA_STORE");
-  if (out16 && c.beta == 0.0 && slices == 1 && !(ts_env && atoi(ts_env) == 0) && ((uintptr_t)c.C % 16 == 0) &&
+  if (out16 && c.beta == 0.0 && slices == 1 && c.n_extra == 0 && !(ts_env && atoi(ts_env) == 0) && ((uintptr_t)c.C % 16 == 0) &&
       (c.ldc * 2) % 16 == 0 && (c.batch == 1 || (c.sc * 2) % 16 == 0) && c.ldc * 2 < ((int64_t)1 << 40) &&
       c.sc * 2 < ((int64_t)1 << 40)) {
     if (make_c_map(&tm.c, 2, dt, c.C, c.m, c.n, c.ldc, c.batch, c.sc)) p.tma_store = 1;

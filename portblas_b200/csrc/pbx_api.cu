@@ -78,6 +78,7 @@ int pbx_destroy(pbx_handle_t h) {
     if (h->aux[i]) cudaFree(h->aux[i]);
   for (int i = 0; i < 2; ++i)
     if (h->lo[i]) cudaFree(h->lo[i]);
+  for (auto& kv : h->ipc_open) cudaIpcCloseMemHandle(kv.second);
   for (cudaEvent_t e : h->events) cudaEventDestroy(e);
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_out) cudaStreamDestroy(h->s_out);
@@ -378,6 +379,92 @@ int pbx_bf16gemm(pbx_handle_t h, char ta, char tb, int64_t m, int64_t n, int64_t
                  const void* A, int64_t lda, int64_t sa, const void* B, int64_t ldb, int64_t sb,
                  const float* beta, void* C, int64_t ldc, int64_t sc, int64_t batch, int bt) {
   return pbx_gemm(h, PBX_BF16, ta, tb, m, n, k, alpha, A, lda, sa, B, ldb, sb, beta, C, ldc, sc, batch, bt);
+}
+
+// ---- multicast GEMM: C <- alpha*op(A)*op(B) + beta*C written into n_dst copies of C at once ---------------------
+// C_list[0] is this GPU's C (read when beta != 0); C_list[1..] are further copies with the same ldc, typically the
+// same row block inside the full C of every peer GPU (pointers from pbx_ipc_import).  On the tcgen05 path the
+// epilogue stores every finished tile to all copies, so the gather of an M-block sharded GEMM costs no extra pass
+// and no collective: NVLink carries tile i while tile i+1 is on the tensor cores.  Other kernels (fp64, tiny or
+// unaligned problems) compute locally and then push the window to the peers with 2-D device-to-device copies.
+int pbx_gemm_multicast(pbx_handle_t h, int dtype, char transa, char transb, int64_t m, int64_t n, int64_t k,
+                       const void* alpha, const void* A, int64_t lda, const void* B, int64_t ldb, const void* beta,
+                       void* const* C_list, int n_dst, int64_t ldc) {
+  if (!h) return PBX_ERR_INVALID_ARG;
+  if (!C_list || n_dst < 1 || n_dst > 8 || !valid_dtype(dtype) || !alpha || !beta || m < 0 || n < 0 || k < 0) {
+    h->last_error = "pbx_gemm_multicast: invalid argument";
+    return PBX_ERR_INVALID_ARG;
+  }
+  if (n_dst == 1)
+    return pbx_gemm(h, dtype, transa, transb, m, n, k, alpha, A, lda, 0, B, ldb, 0, beta, C_list[0], ldc, 0, 1, 0);
+  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  const double al = read_scalar(dtype, alpha), be = read_scalar(dtype, beta);
+  const int ta_c = tolower((unsigned char)transa), tb_c = tolower((unsigned char)transb);
+  const bool plain = (al != 0.0) && (ta_c == 'n' || ta_c == 't' || ta_c == 'c') &&
+                     (tb_c == 'n' || tb_c == 't' || tb_c == 'c') && m > 0 && n > 0 && k > 0 && A && B && C_list[0];
+  int st;
+  if (plain) {
+    PbxGemmCall c;
+    c.dtype = dtype; c.ta = (ta_c != 'n'); c.tb = (tb_c != 'n');
+    c.m = m; c.n = n; c.k = k; c.alpha = al; c.beta = be;
+    c.A = A; c.B = B; c.C = C_list[0]; c.lda = lda; c.ldb = ldb; c.ldc = ldc;
+    c.sa = c.sb = c.sc = 0; c.batch = 1;
+    c.n_extra = n_dst - 1;
+    for (int x = 1; x < n_dst; ++x) c.c_extra[x - 1] = C_list[x];
+    h->last_split_k = 1;
+    st = run_gemm(h, c, 0);
+    if (st != PBX_OK) return st;
+    if (h->last_kernel == PBX_KERNEL_TCGEN05) return PBX_OK;   // the epilogue already wrote every copy
+  } else {   // shortcuts and errors: exactly pbx_gemm's behaviour on the local copy
+    st = pbx_gemm(h, dtype, transa, transb, m, n, k, alpha, A, lda, 0, B, ldb, 0, beta, C_list[0], ldc, 0, 1, 0);
+    if (st != PBX_OK || m == 0 || n == 0) return st;
+  }
+  const size_t eo = pbx_out_size(dtype);
+  for (int x = 1; x < n_dst; ++x)
+    PBX_CUDA_CHECK(h, cudaMemcpy2DAsync(C_list[x], (size_t)ldc * eo, C_list[0], (size_t)ldc * eo, (size_t)m * eo,
+                                        (size_t)n, cudaMemcpyDefault, h->stream));
+  return PBX_OK;
+}
+
+// ---- CUDA IPC: one process per GPU, so a peer's C is reached through an exported allocation handle ---------------
+int pbx_ipc_export(pbx_handle_t h, const void* dptr, void* handle_out, int64_t* offset_out) {
+  if (!h || !dptr || !handle_out || !offset_out) return PBX_ERR_INVALID_ARG;
+  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  // the handle names the whole allocation: find its base (allocator blocks are sub-ranges of one cudaMalloc)
+  typedef CUresult (*range_fn_t)(CUdeviceptr*, size_t*, CUdeviceptr);
+  void* f = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess || !f) {
+    h->last_error = "cuMemGetAddressRange unavailable";
+    return PBX_ERR_CUDA;
+  }
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (reinterpret_cast<range_fn_t>(f)(&base, &size, (CUdeviceptr)dptr) != CUDA_SUCCESS) {
+    h->last_error = "cuMemGetAddressRange failed";
+    return PBX_ERR_CUDA;
+  }
+  PBX_CUDA_CHECK(h, cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle_out), (void*)base));
+  *offset_out = (int64_t)((CUdeviceptr)dptr - base);
+  return PBX_OK;
+}
+
+int pbx_ipc_import(pbx_handle_t h, const void* handle, int64_t offset, void** dptr_out) {
+  if (!h || !handle || !dptr_out || offset < 0) return PBX_ERR_INVALID_ARG;
+  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  const std::string key(reinterpret_cast<const char*>(handle), sizeof(cudaIpcMemHandle_t));
+  void* base = nullptr;
+  for (auto& kv : h->ipc_open)
+    if (kv.first == key) base = kv.second;
+  if (!base) {   // an allocation can be opened once per process: keep it mapped until the handle is destroyed
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle, sizeof(hd));
+    PBX_CUDA_CHECK(h, cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess));
+    h->ipc_open.emplace_back(key, base);
+  }
+  *dptr_out = (char*)base + offset;
+  return PBX_OK;
 }
 
 // ---- memory helpers ------------------------------------------------------------------

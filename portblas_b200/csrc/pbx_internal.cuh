@@ -26,6 +26,9 @@ struct PbxGemmCall {
   int64_t lda, ldb, ldc;
   int64_t sa, sb, sc;  // batch strides in elements (strided)
   int64_t batch;
+  // multicast GEMM (pbx_gemm_multicast): further copies of C that receive every tile (peer GPUs' memory)
+  int n_extra = 0;
+  void* c_extra[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 struct pbx_handle_s {
@@ -55,6 +58,8 @@ struct pbx_handle_s {
   void* aux[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t aux_bytes[4] = {0, 0, 0, 0};
   int conj_transpose = 0;   // complex GEMM: 0 = 'c' behaves as 't' (the reference), 1 = BLAS conjugate-transpose
+  // peer allocations opened through CUDA IPC (pbx_ipc_import): 64-byte handle -> mapped base pointer
+  std::vector<std::pair<std::string, void*>> ipc_open;
   // staging buffers for pbx_gemm_host
   void* stage[3] = {nullptr, nullptr, nullptr};
   int64_t stage_bytes[3] = {0, 0, 0};

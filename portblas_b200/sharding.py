@@ -152,3 +152,28 @@ def gemm_mblock_gather_overlapped(gemm_panel, m: int, n: int, rows: int, world: 
     if cuda:
         main.wait_stream(side_stream)
     return full
+
+
+def share_full_c(sb_handle, c_full: torch.Tensor, group=None) -> List[int]:
+    """Exchange CUDA IPC handles of every rank's full C and map the peers' buffers: returns device pointers
+    (ints) indexed by rank, valid in this process ([rank] is the local tensor itself)."""
+    from . import blas
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    exported = [None] * world
+    dist.all_gather_object(exported, blas.ipc_export(sb_handle, c_full), group=group)
+    return [c_full.data_ptr() if r == rank else blas.ipc_import(sb_handle, exported[r]) for r in range(world)]
+
+
+def gemm_mblock_fused_gather(sb_handle, transa: str, transb: str, m: int, n: int, k: int, alpha, a_local, lda: int, b,
+                             ldb: int, beta, c_ptrs: List[int], ldc: int, c_dtype, world: int, rank: int,
+                             align: int = 128) -> MBlockShard:
+    """This rank's M-block of C <- alpha*op(A)*op(B) + beta*C, written by the GEMM epilogue into the same rows of EVERY
+    rank's full C (``c_ptrs`` from ``share_full_c``): when all ranks have run it and synchronised, each holds the whole
+    result -- the gather costs no pass over C and no collective.  ``a_local`` already points at the rank's rows of A
+    (``shard_mblock(...).a_offset``)."""
+    from . import blas
+    sh = shard_mblock(transa, m, lda, world, rank, align)
+    es = torch.empty(0, dtype=c_dtype).element_size()
+    ptrs = [c_ptrs[rank] + sh.c_offset * es] + [c_ptrs[r] + sh.c_offset * es for r in range(world) if r != rank]
+    blas._gemm_multicast(sb_handle, transa, transb, sh.rows, n, k, alpha, a_local, lda, b, ldb, beta, ptrs, ldc, c_dtype)
+    return sh
