@@ -107,3 +107,53 @@ def test_cgemm_front_end_rules():
     assert ox.cgemm("x", "n", 4, 4, 4, 1 + 0j, z, 4, z, 4, 0j, c, 4) == 1
     assert ox.cgemm("n", "y", 4, 4, 4, 1 + 0j, z, 4, z, 4, 0j, c, 4) == 2
     assert ox.cgemm("n", "n", 4, 4, 4, 1 + 0j, z, 4, z, 4, 0j, c, 4, stridec=3, batch=2) == 3
+
+
+def _golden():
+    from pathlib import Path
+    return np.load(Path(__file__).parent / "golden" / "ext_golden.npz", allow_pickle=False)
+
+
+def test_restatements_reproduce_committed_golden_vectors():
+    """tests/golden/ext_golden.npz (make_golden_ext.py: CBLAS on seeded inputs) against the numpy restatements."""
+    g = _golden()
+    i = 0
+    while f"symm{i}_meta" in g.files:
+        dt, side, uplo, m, n, al, be, la, lb, lc = g[f"symm{i}_meta"]
+        m, n, la, lb, lc = (int(x) for x in (m, n, la, lb, lc))
+        k = m if side == "l" else n
+        c = g[f"symm{i}_C"].copy()
+        assert ox.symm(str(side), str(uplo), m, n, float(al), g[f"symm{i}_A"], k * la, g[f"symm{i}_B"], m * lb, float(be),
+                       c, m * lc) == 0
+        assert oracle.compare(c, g[f"symm{i}_out"], "double" if dt == "f64" else "float") == 0, f"symm case {i}"
+        i += 1
+    assert i >= 5
+    i = 0
+    while f"trsm{i}_meta" in g.files:
+        dt, side, uplo, tr, dg, m, n, al = g[f"trsm{i}_meta"]
+        m, n = int(m), int(n)
+        k = m if side == "l" else n
+        b = g[f"trsm{i}_B"].copy()
+        assert ox.trsm_ref_algorithm(str(side), str(uplo), str(tr), str(dg), m, n, float(al), g[f"trsm{i}_A"], 2 * k, b,
+                                     2 * m) == 0
+        assert oracle.compare(b, g[f"trsm{i}_out"], "double" if dt == "f64" else "float") == 0, f"trsm case {i}"
+        b2 = g[f"trsm{i}_B"].copy()
+        trsm_model(str(side), str(uplo), str(tr), str(dg), m, n, float(al), g[f"trsm{i}_A"], 2 * k, b2, 2 * m,
+                   64 if dt == "f64" else 128)
+        assert oracle.compare(b2, g[f"trsm{i}_out"], "double" if dt == "f64" else "float") == 0, f"trsm model case {i}"
+        i += 1
+    assert i >= 5
+    i = 0
+    while f"cgemm{i}_meta" in g.files:
+        dt, ta, tb, m, n, k, la, lb, lc = g[f"cgemm{i}_meta"]
+        m, n, k, la, lb, lc = (int(x) for x in (m, n, k, la, lb, lc))
+        al, be = (complex(x) for x in g[f"cgemm{i}_scal"])
+        lda, ldb, ldc = (k if ta != "n" else m) * la, (n if tb != "n" else k) * lb, m * lc
+        c = g[f"cgemm{i}_C"].copy()
+        assert ox.cgemm(str(ta), str(tb), m, n, k, al, g[f"cgemm{i}_A"], lda, g[f"cgemm{i}_B"], ldb, be, c, ldc) == 0
+        kind = "double" if dt == "c128" else "float"
+        want = g[f"cgemm{i}_out"]
+        assert oracle.compare(c.real.copy(), want.real.copy(), kind) == 0, f"cgemm case {i}"
+        assert oracle.compare(c.imag.copy(), want.imag.copy(), kind) == 0, f"cgemm case {i}"
+        i += 1
+    assert i >= 4
