@@ -1,0 +1,43 @@
+"""CPU checks of tools/portblas_bench.py, the stand-in for the reference's benchmark/portblas harness: benchmark
+names (common/include/common/benchmark_names.hpp:53-58,190-232) and counters
+(common/include/common/blas3_state_counters.hpp:38-76,141-166) for rows of the reference's CSV parameter files."""
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT / "tools"))
+import portblas_bench as pb  # noqa: E402
+
+
+def test_benchmark_names_follow_the_reference():
+    # benchmark/config_csv/blas3/gemm/*.csv rows are `ta,tb,m,k,n,alpha,beta` (note m,k,n)
+    assert pb.bench_name("gemm", "float", ["n", "N", "1024", "56", "2", "1", "0"]) == "BM_Gemm<float>/n/n/1024/56/2/usm"
+    assert pb.bench_name("gemm", "complex<double>", ["t", "n", 8, 9, 10, 1, 1]) == "BM_Gemm<complex<double>>/t/n/8/9/10/usm"
+    assert pb.bench_name("gemm_batched", "float", ["n", "n", 64, 64, 5000, 1, 0, 32, "interleaved"]) == \
+        "BM_Gemm_batched<float>/n/n/64/64/5000/32/interleaved/usm"
+    assert pb.bench_name("gemm_batched_strided", "half", ["n", "t", 384, 64, 384, 1, 0, 896, 1, 2, 3]) == \
+        "BM_Gemm_batched_strided<half>/n/t/384/64/384/896/1/2/3/usm"
+    assert pb.bench_name("symm", "double", ["l", "u", 256, 512, 1, 0]) == "BM_Symm<double>/l/u/256/512/1/0/usm"
+    assert pb.bench_name("symm", "float", ["R", "L", 16, 8, 1.5, 0.5]) == "BM_Symm<float>/r/l/16/8/1.5/0.5/usm"
+    assert pb.bench_name("trsm", "float", ["l", "u", "n", "n", 345, 560, 1]) == "BM_Trsm<float>/l/u/n/n/345/560/usm"
+
+
+def test_counters_follow_the_reference():
+    c = pb.counters("gemm", "float", ["n", "n", 4, 3, 2, 1, 1])          # m=4 k=3 n=2, beta != 0
+    assert c["n_fl_ops"] == 2 * 3 * 4 * 2 + 4 * 2 + 2 * 4 * 2 and c["bytes_processed"] == (12 + 6 + 8 + 8) * 4
+    c = pb.counters("gemm", "double", ["n", "n", 4, 3, 2, 1, 0])         # beta == 0: C is not read
+    assert c["n_fl_ops"] == 48 + 8 and c["bytes_processed"] == (12 + 6 + 8) * 8
+    c = pb.counters("gemm_batched_strided", "half", ["n", "n", 4, 3, 2, 1, 0, 5, 2, 2, 2])
+    assert c["batch_size"] == 5 and c["stride_c_mul"] == 2 and c["n_fl_ops"] == 56 * 5 and c["bytes_processed"] == 26 * 5 * 2
+    c = pb.counters("symm", "float", ["r", "u", 4, 3, 1, 0])
+    assert c["n_fl_ops"] == 2 * 3 * 3 * 3 and c["bytes_processed"] == (12 + 12 + 6) * 4
+    c = pb.counters("trsm", "double", ["l", "l", "n", "n", 4, 3, 1])
+    assert c["k"] == 4 and c["n_fl_ops"] == 16 * 3 + 12
+
+
+def test_fixture_rows_map_to_names():
+    import json
+    rows = json.loads((ROOT / "tests" / "golden" / "config_csv_shapes.json").read_text())["rows"]
+    r = next(x for x in rows if x["api"] == "gemm")
+    name = pb.bench_name("gemm", "float", [r["ta"], r["tb"], r["m"], r["k"], r["n"], r["alpha"], r["beta"]])
+    assert name == f"BM_Gemm<float>/{r['ta']}/{r['tb']}/{r['m']}/{r['k']}/{r['n']}/usm"

@@ -28,14 +28,11 @@ import sys
 import time
 from pathlib import Path
 
-import torch
-
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
-from portblas_b200 import SB_Handle, blas, gemm_batch_type_t  # noqa: E402
 
-TYPES = {"float": torch.float32, "double": torch.float64, "half": torch.float16, "bfloat16": torch.bfloat16,
-         "complex<float>": torch.complex64, "complex<double>": torch.complex128}
+TYPE_NAMES = ["float", "double", "half", "bfloat16", "complex<float>", "complex<double>"]
+TYPE_BYTES = {"float": 4, "double": 8, "half": 2, "bfloat16": 2, "complex<float>": 8, "complex<double>": 16}
 OP_NAME = {"gemm": "Gemm", "gemm_batched": "Gemm_batched", "gemm_batched_strided": "Gemm_batched_strided",
            "symm": "Symm", "trsm": "Trsm"}
 DEFAULTS = {  # a small default sweep when no CSV is given (the reference's defaults are {32,256,2048}^3 x all trans)
@@ -52,13 +49,70 @@ def fmt_scalar(v: float) -> str:
 
 
 def rand(count, dt, dev):
+    import torch
     if dt.is_complex:
         return torch.complex(torch.rand(count, device=dev) * 7 - 2, torch.rand(count, device=dev) * 7 - 2).to(dt)
     return (torch.rand(count, device=dev, dtype=torch.float32) * 7 - 2).to(dt)
 
 
+def bench_name(op, tname, row) -> str:
+    """The reference's benchmark name for one parameter row (benchmark_names.hpp:53-58,190-232; mem type "usm")."""
+    if op == "gemm":
+        body = f"{row[0].lower()}/{row[1].lower()}/{int(row[2])}/{int(row[3])}/{int(row[4])}"
+    elif op == "gemm_batched":
+        body = (f"{row[0].lower()}/{row[1].lower()}/{int(row[2])}/{int(row[3])}/{int(row[4])}/{int(row[7])}/"
+                f"{str(row[8]).strip().lower()}")
+    elif op == "gemm_batched_strided":
+        body = (f"{row[0].lower()}/{row[1].lower()}/{int(row[2])}/{int(row[3])}/{int(row[4])}/{int(row[7])}/"
+                f"{int(row[8])}/{int(row[9])}/{int(row[10])}")
+    elif op == "symm":
+        body = (f"{row[0].lower()}/{row[1].lower()}/{int(row[2])}/{int(row[3])}/{fmt_scalar(float(row[4]))}/"
+                f"{fmt_scalar(float(row[5]))}")
+    elif op == "trsm":
+        body = f"{row[0].lower()}/{row[1].lower()}/{row[2].lower()}/{row[3].lower()}/{int(row[4])}/{int(row[5])}"
+    else:
+        raise ValueError(op)
+    return f"BM_{OP_NAME[op]}<{tname}>/{body}/usm"
+
+
+def counters(op, tname, row) -> dict:
+    """n_fl_ops / bytes_processed (+ the shape counters) of blas3_state_counters.hpp:38-76 (gemm family, complex
+    variant :79-135), :141-166 (symm) and the trsm counters of benchmark/portblas/blas3/trsm.cpp."""
+    es = TYPE_BYTES[tname]
+    cplx = tname.startswith("complex")
+    if op.startswith("gemm"):
+        m, k, n = int(row[2]), int(row[3]), int(row[4])
+        beta = float(row[6])
+        batch = int(row[7]) if op != "gemm" else 1
+        b0 = beta != 0
+        cnt = dict(beta=beta, m=m, n=n, k=k, batch_size=batch)
+        if op == "gemm_batched_strided":
+            cnt.update(stride_a_mul=int(row[8]), stride_b_mul=int(row[9]), stride_c_mul=int(row[10]))
+        if cplx:   # 4 mul + 4 add per complex multiply-add, 6 per complex scaling
+            cnt["n_fl_ops"] = (8.0 * k * m * n + 6.0 * m * n + (8.0 * m * n if b0 else 0)) * batch
+        else:
+            cnt["n_fl_ops"] = (2.0 * k * m * n + m * n + (2.0 * m * n if b0 else 0)) * batch
+        cnt["bytes_processed"] = float((m * k + k * n + m * n + (m * n if b0 else 0)) * batch * es)
+        return cnt
+    if op == "symm":
+        side, m, n, beta = row[0].lower(), int(row[2]), int(row[3]), float(row[5])
+        kk = m if side == "l" else n
+        b0 = beta != 0
+        return dict(beta=beta, m=m, n=n,
+                    n_fl_ops=(2.0 * m * m * n if side == "l" else 2.0 * n * n * n) + (2.0 * m * n if b0 else 0),
+                    bytes_processed=float(((2 if b0 else 1) * m * n + m * n + kk * (kk + 1) / 2) * es))
+    if op == "trsm":
+        side, m, n = row[0].lower(), int(row[4]), int(row[5])
+        kk = m if side == "l" else n
+        return dict(m=m, n=n, k=kk, n_fl_ops=float(kk) * kk * (n if side == "l" else m) + m * n,
+                    bytes_processed=float((kk * (kk + 1) / 2 + 2 * m * n) * es))
+    raise ValueError(op)
+
+
 def build_case(op, tname, dt, row, h, dev):
     """Returns (benchmark name, counters, callable)."""
+    import torch
+    from portblas_b200 import blas, gemm_batch_type_t
     es = torch.empty(0, dtype=dt).element_size()
     if op.startswith("gemm"):
         ta, tb = row[0].lower(), row[1].lower()
@@ -77,35 +131,21 @@ def build_case(op, tname, dt, row, h, dev):
         if dt.is_complex:
             alpha, beta = complex(alpha, 0), complex(beta, 0)
         if op == "gemm":
-            name = f"{ta}/{tb}/{m}/{k}/{n}"
             fn = lambda: blas._gemm(h, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc)  # noqa: E731
         elif op == "gemm_batched":
-            name = f"{ta}/{tb}/{m}/{k}/{n}/{batch}/{bt}"
             btype = gemm_batch_type_t.interleaved if bt == "interleaved" else gemm_batch_type_t.strided
             fn = lambda: blas._gemm_batched(h, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, batch, btype)  # noqa: E731
         else:
-            name = f"{ta}/{tb}/{m}/{k}/{n}/{batch}/{sm[0]}/{sm[1]}/{sm[2]}"
             fn = lambda: blas._gemm_strided_batched(h, ta, tb, m, n, k, alpha, a, lda, sa, b, ldb, sb, beta, c, ldc,  # noqa: E731
                                                     sc, batch)
-        b0 = beta != 0
-        cnt = dict(beta=float(abs(beta)) if dt.is_complex else beta, m=m, n=n, k=k, batch_size=batch)
-        if dt.is_complex:   # init_level_3_cplx_counters: 4 mul + 4 add per complex multiply-add
-            cnt["n_fl_ops"] = (8.0 * k * m * n + 6.0 * m * n + (8.0 * m * n if b0 else 0)) * batch
-        else:
-            cnt["n_fl_ops"] = (2.0 * k * m * n + m * n + (2.0 * m * n if b0 else 0)) * batch
-        cnt["bytes_processed"] = float((m * k + k * n + m * n + (m * n if b0 else 0)) * batch * es)
-        return f"BM_{OP_NAME[op]}<{tname}>/{name}/usm", cnt, fn
+        return bench_name(op, tname, row), counters(op, tname, row), fn
     if op == "symm":
         side, uplo, m, n, alpha, beta = row[0].lower(), row[1].lower(), int(row[2]), int(row[3]), float(row[4]), float(row[5])
         kk = m if side == "l" else n
         a, b = rand(kk * kk, dt, dev), rand(m * n, dt, dev)
         c = torch.zeros(m * n, device=dev, dtype=dt)
         fn = lambda: blas._symm(h, side, uplo, m, n, alpha, a, kk, b, m, beta, c, m)  # noqa: E731
-        b0 = beta != 0
-        cnt = dict(beta=beta, m=m, n=n)
-        cnt["n_fl_ops"] = (2.0 * m * m * n if side == "l" else 2.0 * n * n * n) + (2.0 * m * n if b0 else 0)
-        cnt["bytes_processed"] = float(((2 if b0 else 1) * m * n + m * n + kk * (kk + 1) / 2) * es)
-        return f"BM_Symm<{tname}>/{side}/{uplo}/{m}/{n}/{fmt_scalar(alpha)}/{fmt_scalar(beta)}/usm", cnt, fn
+        return bench_name(op, tname, row), counters(op, tname, row), fn
     if op == "trsm":
         side, uplo, tr, dg, m, n = row[0].lower(), row[1].lower(), row[2].lower(), row[3].lower(), int(row[4]), int(row[5])
         alpha = float(row[6]) if len(row) > 6 else 1.0
@@ -119,15 +159,12 @@ def build_case(op, tname, dt, row, h, dev):
 
         def fn():
             blas._trsm(h, side, uplo, tr, dg, m, n, alpha, a, kk, b, m)
-        cnt = dict(m=m, n=n, k=kk)
-        # blas3_state_counters.hpp trsm: k*k*(m or n) multiply-adds on the triangle + alpha
-        cnt["n_fl_ops"] = float(kk) * kk * (n if side == "l" else m) + m * n
-        cnt["bytes_processed"] = float((kk * (kk + 1) / 2 + 2 * m * n) * es)
-        return f"BM_Trsm<{tname}>/{side}/{uplo}/{tr}/{dg}/{m}/{n}/usm", cnt, fn
+        return bench_name(op, tname, row), counters(op, tname, row), fn
     raise ValueError(op)
 
 
 def run_case(h, name, cnt, fn, min_time, max_iters):
+    import torch
     for _ in range(10):   # warmup (common_utils.hpp:1841-1845)
         fn()
     h.wait()
@@ -193,11 +230,15 @@ def main():
             rows = [r for r in csv.reader(f) if r and not r[0].startswith("#")]
     if args.max_rows:
         rows = rows[:args.max_rows]
+    import torch
+    from portblas_b200 import SB_Handle
+    types = {"float": torch.float32, "double": torch.float64, "half": torch.float16, "bfloat16": torch.bfloat16,
+             "complex<float>": torch.complex64, "complex<double>": torch.complex128}
     dev = torch.device("cuda", 0)
     h = SB_Handle(0)
     results = []
     for tname in args.types.split(","):
-        dt = TYPES[tname.strip()]
+        dt = types[tname.strip()]
         for row in rows:
             if args.op.startswith("gemm"):
                 m_, k_, n_ = int(row[2]), int(row[3]), int(row[4])
