@@ -112,6 +112,10 @@ int pbx_last_repack(pbx_handle_t h);               /* bit 0 / 1: A / B was re-la
 int pbx_last_presplit(pbx_handle_t h);             /* fp32 mode of the last call: 0 in-kernel 3xTF32 split, 1 pre-split lo halves, 2 single tf32 (SB_ENABLE_JOINT_MATRIX=1) */
 int64_t pbx_launch_count(pbx_handle_t h);          /* kernels launched through this handle so far */
 int64_t pbx_workspace_bytes(pbx_handle_t h);       /* current size of the pooled workspace */
+/* The tensor-core tile plan for a shape as a pure function (no device, no handle): CTA group (1 or 2), tile width,
+ * K slices, skinny-M operand swap.  What replaces the reference's shape heuristics (nvidia_gpu.hpp:116-171).   */
+int pbx_plan_query(int sm_count, int dtype, int64_t m, int64_t n, int64_t k, int64_t batch, int* cta_group,
+                   int* tile_n, int* k_slices, int* swapped);
 
 /* ---- the GEMM entry point ------------------------------------------------
  *  C_b <- alpha * op(A_b) * op(B_b) + beta * C_b      b = 0 .. batch-1

@@ -40,6 +40,8 @@ SYMBOLS = {
     "pbx_last_presplit": (c_int, [c_void_p]),
     "pbx_launch_count": (c_int64, [c_void_p]),
     "pbx_workspace_bytes": (c_int64, [c_void_p]),
+    "pbx_plan_query": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, c_int64, POINTER(c_int), POINTER(c_int),
+                               POINTER(c_int), POINTER(c_int)]),
     "pbx_gemm": (c_int, [c_void_p, c_int, c_char, c_char] + _GEMM_TAIL),
     "pbx_sgemm": (c_int, [c_void_p, c_char, c_char] + _GEMM_TAIL),
     "pbx_dgemm": (c_int, [c_void_p, c_char, c_char] + _GEMM_TAIL),

@@ -802,6 +802,24 @@ bool pbx_tcgen05_eligible(pbx_handle_t h, const PbxGemmCall& c) {
 
 int pbx_tcgen05_slices(pbx_handle_t h, const PbxGemmCall& c) { return make_plan(h, c).slices; }
 
+// The tile plan as a pure function of the shape (no device needed): lets the CPU test-suite pin the selector.
+extern "C" int pbx_plan_query(int sm_count, int dtype, int64_t m, int64_t n, int64_t k, int64_t batch, int* cta_group,
+                              int* tile_n, int* k_slices, int* swapped) {
+  if (sm_count <= 0 || dtype < PBX_F32 || dtype > PBX_BF16_F32 || dtype == PBX_F64 || m <= 0 || n <= 0 || k <= 0 ||
+      batch <= 0 || !cta_group || !tile_n || !k_slices || !swapped)
+    return PBX_ERR_INVALID_ARG;
+  pbx_handle_s fake;
+  fake.sm_count = sm_count;
+  PbxGemmCall c;
+  c.dtype = dtype; c.ta = c.tb = false;
+  c.m = m; c.n = n; c.k = k; c.alpha = 1.0; c.beta = 0.0;
+  c.A = c.B = nullptr; c.C = nullptr;
+  c.lda = m; c.ldb = k; c.ldc = m; c.sa = m * k; c.sb = k * n; c.sc = m * n; c.batch = batch;
+  const TcPlan p = make_plan(&fake, c);
+  *cta_group = p.cg; *tile_n = p.bn; *k_slices = p.slices; *swapped = p.swap ? 1 : 0;
+  return PBX_OK;
+}
+
 int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
   const int es = (int)pbx_in_size(c.dtype);
   const bool f32 = (c.dtype == PBX_F32);

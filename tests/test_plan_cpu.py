@@ -1,0 +1,72 @@
+"""CPU tests of the tensor-core tile selector (pbx_plan_query -> gemm_tcgen05.cu:make_plan), the replacement of the
+reference's NVIDIA shape heuristics (src/interface/blas3/backend/nvidia_gpu.hpp:116-171) and of its tall-skinny rule
+(gemm_partial_local.hpp:191-199, portblas_handle.hpp:323).  No device is needed: the plan is a pure function of the
+shape and the SM count."""
+import ctypes
+
+import pytest
+
+from portblas_b200 import _lib
+
+F32, F16, BF16 = _lib.F32, _lib.F16, _lib.BF16
+
+
+def plan(pbx_lib, dt, m, n, k, batch=1, sms=148):
+    cg, bn, sl, sw = (ctypes.c_int() for _ in range(4))
+    st = pbx_lib.pbx_plan_query(sms, dt, m, n, k, batch, ctypes.byref(cg), ctypes.byref(bn), ctypes.byref(sl),
+                                ctypes.byref(sw))
+    assert st == 0
+    return cg.value, bn.value, sl.value, bool(sw.value)
+
+
+def test_baseline_configs(pbx_lib):
+    # cfg3 SGEMM 16384^3 and its 8-GPU M-block shard: CTA pairs on 256x256 tiles, no split
+    assert plan(pbx_lib, F32, 16384, 16384, 16384) == (2, 256, 1, False)
+    assert plan(pbx_lib, F32, 2048, 16384, 16384) == (2, 256, 1, False)
+    # cfg4: HBM-bound 16-bit batches -> 148 independent single-CTA tiles
+    assert plan(pbx_lib, BF16, 256, 256, 256, 4096) == (1, 128, 1, False)
+    assert plan(pbx_lib, F16, 256, 256, 256, 512) == (1, 128, 1, False)
+    # compute-bound 16-bit: CTA pairs
+    assert plan(pbx_lib, BF16, 8192, 8192, 8192) == (2, 256, 1, False)
+    # cfg5 tall-skinny: 4 pair tiles spread over 74 pairs x 2 waves of K slices
+    cg, bn, slices, swapped = plan(pbx_lib, F32, 512, 512, 1 << 20)
+    assert (cg, bn, swapped) == (2, 256, False) and slices == 37
+    # cfg1 shape: 64 single-CTA tiles cannot fill 148 SMs -> split K four ways
+    assert plan(pbx_lib, F32, 1024, 1024, 1024) == (1, 128, 4, False)
+
+
+def test_skinny_m_swaps_operands(pbx_lib):
+    cg, bn, slices, swapped = plan(pbx_lib, F32, 40, 1000, 520)
+    assert (cg, bn, swapped) == (1, 64, True)
+    assert plan(pbx_lib, F32, 64, 401408, 1152)[3] is True
+    assert plan(pbx_lib, F32, 65, 401408, 1152)[3] is False          # only M <= 64
+    assert plan(pbx_lib, F32, 40, 30, 520)[3] is False               # and only when N > M
+
+
+def test_split_k_rules(pbx_lib):
+    # never more slices than K blocks / 4, never for short K loops, never when the tiles already fill the machine
+    for dt, kblock in ((F32, 32), (BF16, 64)):
+        for m, n, k in [(128, 128, 3136), (64, 64, 784), (256, 196, 2304), (512, 512, 65536), (4096, 4096, 4096),
+                        (128, 128, 256), (300, 260, 4104)]:
+            cg, bn, slices, _ = plan(pbx_lib, dt, m, n, k)
+            kb = -(-k // kblock)
+            assert 1 <= slices <= max(1, kb // 4) or slices == 1
+            tiles = -(-m // (128 * cg)) * -(-n // bn)
+            if tiles * 2 > 148 // cg or kb < 16:
+                assert slices == 1, (dt, m, n, k, slices)
+    assert plan(pbx_lib, F32, 128, 128, 3136)[2] > 1
+    assert plan(pbx_lib, F32, 4096, 4096, 4096)[2] == 1
+
+
+def test_plan_scales_with_sm_count(pbx_lib):
+    # a smaller part needs fewer tiles to be "full": the same shape stops splitting
+    assert plan(pbx_lib, F32, 1024, 1024, 1024, sms=148)[2] > 1
+    assert plan(pbx_lib, F32, 1024, 1024, 1024, sms=32)[2] == 1
+
+
+def test_invalid_queries(pbx_lib):
+    z = ctypes.c_int()
+    args = [ctypes.byref(z)] * 4
+    assert pbx_lib.pbx_plan_query(0, F32, 8, 8, 8, 1, *args) == 6
+    assert pbx_lib.pbx_plan_query(148, _lib.F64, 8, 8, 8, 1, *args) == 6      # fp64 runs on the DMMA kernel
+    assert pbx_lib.pbx_plan_query(148, F32, 0, 8, 8, 1, *args) == 6
