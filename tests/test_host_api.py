@@ -19,6 +19,19 @@ def test_host_callers_compile():
         assert (ROOT / "build" / "ref_sample_gemm") in built
 
 
+def test_api_signatures_compile_for_every_container_and_type():
+    """tests/cpp/api_signatures.cpp instantiates _gemm / _gemm_batched / _gemm_strided_batched / _symm / _trsm with the
+    container kinds and element types of the reference's explicit instantiations (gemm.cpp.in:33-137) and
+    static_asserts the return types and defaults; it must compile, link and run (it executes nothing) on CPU."""
+    from portblas_b200 import build, build_host
+    build.build()
+    exe = ROOT / "build" / "api_signatures"
+    (ROOT / "build").mkdir(exist_ok=True)
+    build_host._compile(ROOT / "tests" / "cpp" / "api_signatures.cpp", exe)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+
+
 @pytest.mark.gpu
 def test_own_cpp_caller_runs(handle):
     from portblas_b200 import build_host
