@@ -5,6 +5,7 @@
 #pragma once
 #include <sycl/sycl.hpp>
 
+#include <complex>
 #include <stdexcept>
 #include <type_traits>
 #include <vector>
@@ -29,6 +30,15 @@ template <typename T> struct ValueType<const T*> { using type = std::remove_cv_t
 
 template <typename T, typename U> struct RebindType { using type = U; };
 template <typename T, typename U> struct RebindType<T*, U> { using type = U*; };
+
+// complex element types (reference include/blas_meta.h:205-225, BLAS_ENABLE_COMPLEX builds)
+template <typename T> using complex_sycl = typename sycl::ext::oneapi::experimental::complex<T>;
+template <class type>
+struct is_complex_sycl : std::integral_constant<bool, std::is_same_v<type, complex_sycl<double>> ||
+                                                          std::is_same_v<type, complex_sycl<float>>> {};
+template <class type>
+struct is_complex_std : std::integral_constant<bool, std::is_same_v<type, std::complex<double>> ||
+                                                         std::is_same_v<type, std::complex<float>>> {};
 
 struct unsupported_exception : public std::runtime_error {
   unsupported_exception(const char* msg = "Unsupported operation") : std::runtime_error(msg) {}

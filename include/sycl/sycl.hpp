@@ -29,7 +29,13 @@
 #include <unordered_map>
 #include <vector>
 
+#include <complex>
+#include <ostream>
+
 #include "../pbx_gemm.h"
+
+// sycl::half streams like a float (callers print mismatching elements, common/include/common/float_comparison.hpp:211)
+inline std::ostream& operator<<(std::ostream& os, const __half& v) { return os << __half2float(v); }
 
 namespace sycl {
 
@@ -49,7 +55,7 @@ enum class aspect { fp16, fp64, gpu, cpu };
 namespace usm { enum class alloc { host, device, shared, unknown }; }
 
 namespace info {
-enum class device_type { cpu, gpu, accelerator, all };
+enum class device_type { cpu, gpu, accelerator, custom, automatic, host, all };
 enum class local_mem_type { none, local, global };
 namespace device {
 struct name { using return_type = std::string; };
@@ -74,8 +80,10 @@ struct property_list {
   template <typename... Ts> property_list(Ts...) {}
 };
 
-struct default_selector_t {};
-struct gpu_selector_t {};
+class device;
+// selectors are callables scoring a device (SYCL 2020): everything here is the one CUDA device of the queue
+struct default_selector_t { int operator()(const device&) const { return 1; } };
+struct gpu_selector_t { int operator()(const device&) const { return 1; } };
 inline constexpr default_selector_t default_selector_v{};
 inline constexpr gpu_selector_t gpu_selector_v{};
 
@@ -236,8 +244,9 @@ class queue {
   queue() : impl_(std::make_shared<detail::queue_impl>(0)) {}
   template <typename Selector, typename = std::enable_if_t<!std::is_same_v<std::decay_t<Selector>, queue>>>
   explicit queue(const Selector&, const property_list& = {}) : queue() {}
-  template <typename Selector>
-  queue(const Selector&, async_handler h, const property_list& = {}) : queue() { impl_->handler = std::move(h); }
+  template <typename Selector, typename Handler,
+            typename = std::enable_if_t<std::is_invocable_v<Handler, exception_list>>>
+  queue(const Selector&, Handler h, const property_list& = {}) : queue() { impl_->handler = async_handler(std::move(h)); }
   queue(const device&, const property_list& = {}) : queue() {}
 
   pbx_handle_t pbx() const { return impl_->h; }
@@ -379,5 +388,11 @@ class buffer {
   }
   bool operator==(const buffer& o) const { return impl_ == o.impl_; }
 };
+
+// sycl::ext::oneapi::experimental::complex<T> (the reference's complex_sycl, include/blas_meta.h:207-209): same layout
+// as std::complex<T>, which is all the GEMM path needs
+namespace ext { namespace oneapi { namespace experimental {
+template <typename T> using complex = std::complex<T>;
+} } }  // namespace ext::oneapi::experimental
 
 }  // namespace sycl

@@ -4,6 +4,12 @@
   build/ref_sample_gemm  the REFERENCE's samples/gemm.cpp compiled UNCHANGED from
                          /root/reference (only when that tree is present: it proves the drop-in
                          claim "existing callers relink unchanged"; the source is not copied)
+  build/ref_unittest_*   the REFERENCE's own unit tests -- test/unittest/main.cpp + test/unittest/blas3/
+                         {blas3_gemm,blas3_gemm_batched,blas3_gemm_tall_skinny,blas3_symm,blas3_trsm}_test.cpp --
+                         compiled UNCHANGED from /root/reference with the compile definitions its CMake uses
+                         (test/unittest/CMakeLists.txt:109-133), against include/, a minimal GoogleTest stand-in
+                         (tests/cpp/shim/gtest/gtest.h), the reference's vendored cblas.h / clara.hpp and the
+                         OpenBLAS of this image as the CBLAS the tests compare with
 
     python -m portblas_b200.build_host
 """
@@ -30,6 +36,46 @@ def _compile(src: Path, exe: Path, extra_inc=()) -> None:
         raise RuntimeError(f"host build failed for {src}:\n{r.stdout}\n{r.stderr}")
 
 
+SCIPY_LIBS = Path(sys.prefix) / "lib" / f"python{sys.version_info.major}.{sys.version_info.minor}" / "site-packages" / "scipy.libs"
+
+# reference unit-test sources -> extra compile definitions (test/unittest/CMakeLists.txt:109-133: half only for the
+# HALF_DATA_OPS list, complex only for executables whose name contains "gemm")
+REF_UNITTESTS = {
+    "blas3_gemm_test": ["-DBLAS_ENABLE_HALF=1", "-DBLAS_ENABLE_COMPLEX=1"],
+    "blas3_gemm_batched_test": ["-DBLAS_ENABLE_HALF=1", "-DBLAS_ENABLE_COMPLEX=1"],
+    "blas3_gemm_tall_skinny_test": ["-DBLAS_ENABLE_COMPLEX=1"],
+    "blas3_symm_test": [],
+    "blas3_trsm_test": [],
+}
+
+
+def build_reference_unittests() -> list:
+    """The reference's own blas3 unit tests, unchanged, against this repository's headers and library."""
+    openblas = sorted(SCIPY_LIBS.glob("libscipy_openblas*.so"))
+    if not (REF / "test" / "unittest" / "main.cpp").exists() or not openblas:
+        return []
+    shim = ROOT / "tests" / "cpp" / "shim"
+    built = []
+    for name, defs in REF_UNITTESTS.items():
+        exe = OUT / f"ref_unittest_{name}"
+        srcs = [REF / "test" / "unittest" / "main.cpp", REF / "test" / "unittest" / "blas3" / f"{name}.cpp"]
+        newest = max(p.stat().st_mtime for p in [*srcs, *ROOT.glob("include/**/*.h*"), *shim.rglob("*.h"), HERE / "libpbx_gemm.so"])
+        if exe.exists() and exe.stat().st_mtime >= newest:
+            built.append(exe)
+            continue
+        cmd = [CXX, "-std=c++17", "-O1", "-I", str(ROOT / "include"), "-I", "/usr/local/cuda/include", "-I", str(shim),
+               "-I", str(REF / "test"), "-I", str(REF / "common" / "include"), "-I", str(REF / "external" / "cblas" / "include"),
+               "-I", str(REF / "external" / "clara" / "include"), "-include", str(shim / "cblas_scipy_rename.h"),
+               "-DBLAS_INDEX_T=int", "-DBLAS_DATA_TYPE_DOUBLE", "-DSB_ENABLE_USM", *defs, *[str(s) for s in srcs],
+               "-o", str(exe), "-L", str(HERE), "-lpbx_gemm", f"-Wl,-rpath,{HERE}", "-L", str(SCIPY_LIBS),
+               f"-l:{openblas[0].name}", f"-Wl,-rpath,{SCIPY_LIBS}"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"reference unit test {name} does not build against include/:\n{r.stderr[-4000:]}")
+        built.append(exe)
+    return built
+
+
 def build() -> list:
     from . import build as libbuild
     libbuild.build()
@@ -45,6 +91,7 @@ def build() -> list:
         exe = OUT / "ref_sample_gemm"
         _compile(ref_src, exe, extra_inc=[REF / "samples"])
         built.append(exe)
+    built += build_reference_unittests()
     return built
 
 

@@ -32,6 +32,31 @@ def test_api_signatures_compile_for_every_container_and_type():
     assert r.returncode == 0, r.stderr
 
 
+def test_reference_unit_tests_compile_unchanged():
+    """The reference's OWN blas3 unit tests (test/unittest/main.cpp + blas3_{gemm,gemm_batched,gemm_tall_skinny,symm,
+    trsm}_test.cpp, incl. the half and complex instantiations its CMake enables) compile UNCHANGED against include/ with
+    a GoogleTest stand-in, link against libpbx_gemm.so and enumerate the reference's test names.  (They need
+    /root/reference at build time; the binaries travel to the GPU box and run there: test_zz_reference_unittests_gpu.py.)"""
+    if not Path("/root/reference/test/unittest/main.cpp").exists():
+        pytest.skip("the reference tree is not present")
+    from portblas_b200 import build, build_host
+    build.build()
+    (ROOT / "build").mkdir(exist_ok=True)
+    built = build_host.build_reference_unittests()
+    assert len(built) == 5
+    want_at_least = {"blas3_gemm_test": 3000, "blas3_gemm_batched_test": 10000, "blas3_gemm_tall_skinny_test": 300,
+                     "blas3_symm_test": 900, "blas3_trsm_test": 1100}
+    for exe in built:
+        r = subprocess.run([str(exe), "--gtest_list_tests"], capture_output=True, text=True, timeout=120)
+        names = [ln for ln in r.stdout.splitlines() if "/" in ln and ".test/" in ln]
+        key = exe.name.replace("ref_unittest_", "")
+        assert len(names) >= want_at_least[key], (exe.name, len(names))
+    r = subprocess.run([str(ROOT / "build" / "ref_unittest_blas3_gemm_test"), "--gtest_list_tests"], capture_output=True,
+                       text=True, timeout=120)
+    assert ("Gemm/GemmSmallBetaNonZeroLDMatchFloatFloat.test/alloc_usm__offset_0__batch_1__m_11__n_11__k_16__transa_n__"
+            "transb_n__alpha_1p50__beta_1p50__ldaMul_1__ldbMul_1__ldcMul_1__batchType_0") in r.stdout
+
+
 @pytest.mark.gpu
 def test_own_cpp_caller_runs(handle):
     from portblas_b200 import build_host
