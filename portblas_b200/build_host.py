@@ -11,6 +11,14 @@
                          (tests/cpp/shim/gtest/gtest.h), the reference's vendored cblas.h / clara.hpp and the
                          OpenBLAS of this image as the CBLAS the tests compare with
 
+  build/ref_bench_*      the REFERENCE's own benchmark harness -- benchmark/portblas/main.cpp + benchmark/portblas/blas3/
+                         {gemm,gemm_batched,gemm_batched_strided,symm,trsm}.cpp -- compiled UNCHANGED from
+                         /root/reference with the definitions of benchmark/portblas/CMakeLists.txt:99-133
+                         (BLAS_VERIFY_BENCHMARK on, the reference's default: every benchmark first checks its result
+                         against CBLAS), against include/, a minimal Google Benchmark stand-in
+                         (tests/cpp/shim/benchmark/benchmark.h: console + JSON reports, --benchmark_filter/min_time/out)
+                         and tests/cpp/shim/bench_info_stub.cc for the two labels the reference generates at configure time
+
     python -m portblas_b200.build_host
 """
 from __future__ import annotations
@@ -76,6 +84,45 @@ def build_reference_unittests() -> list:
     return built
 
 
+# reference benchmark sources -> extra compile definitions (benchmark/portblas/CMakeLists.txt:99-133: complex for
+# CPLX_OPS, half for HALF_DATA_OPS)
+REF_BENCHMARKS = {
+    "gemm": ["-DBLAS_ENABLE_HALF=1", "-DBLAS_ENABLE_COMPLEX=1"],
+    "gemm_batched": ["-DBLAS_ENABLE_HALF=1", "-DBLAS_ENABLE_COMPLEX=1"],
+    "gemm_batched_strided": ["-DBLAS_ENABLE_HALF=1", "-DBLAS_ENABLE_COMPLEX=1"],
+    "symm": [],
+    "trsm": [],
+}
+
+
+def build_reference_benchmarks() -> list:
+    """The reference's own benchmark executables (bench_gemm ...), unchanged, against this repository's headers and library."""
+    openblas = sorted(SCIPY_LIBS.glob("libscipy_openblas*.so"))
+    bdir = REF / "benchmark" / "portblas"
+    if not (bdir / "main.cpp").exists() or not openblas:
+        return []
+    shim = ROOT / "tests" / "cpp" / "shim"
+    built = []
+    for name, defs in REF_BENCHMARKS.items():
+        exe = OUT / f"ref_bench_{name}"
+        srcs = [bdir / "main.cpp", bdir / "blas3" / f"{name}.cpp", shim / "bench_info_stub.cc"]
+        newest = max(p.stat().st_mtime for p in [*srcs, *ROOT.glob("include/**/*.h*"), *shim.rglob("*.h"), HERE / "libpbx_gemm.so"])
+        if exe.exists() and exe.stat().st_mtime >= newest:
+            built.append(exe)
+            continue
+        cmd = [CXX, "-std=c++17", "-O1", "-I", str(ROOT / "include"), "-I", "/usr/local/cuda/include", "-I", str(shim),
+               "-I", str(bdir), "-I", str(REF / "common" / "include"), "-I", str(REF / "external" / "cblas" / "include"),
+               "-I", str(REF / "external" / "clara" / "include"), "-include", str(shim / "cblas_scipy_rename.h"),
+               "-DBLAS_INDEX_T=int", "-DBLAS_DATA_TYPE_DOUBLE", "-DSB_ENABLE_USM", "-DBLAS_VERIFY_BENCHMARK", *defs,
+               *[str(s) for s in srcs], "-o", str(exe), "-L", str(HERE), "-lpbx_gemm", f"-Wl,-rpath,{HERE}",
+               "-L", str(SCIPY_LIBS), f"-l:{openblas[0].name}", f"-Wl,-rpath,{SCIPY_LIBS}"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"reference benchmark {name} does not build against include/:\n{r.stderr[-4000:]}")
+        built.append(exe)
+    return built
+
+
 def build() -> list:
     from . import build as libbuild
     libbuild.build()
@@ -92,6 +139,7 @@ def build() -> list:
         _compile(ref_src, exe, extra_inc=[REF / "samples"])
         built.append(exe)
     built += build_reference_unittests()
+    built += build_reference_benchmarks()
     return built
 
 

@@ -57,6 +57,27 @@ def test_reference_unit_tests_compile_unchanged():
             "transb_n__alpha_1p50__beta_1p50__ldaMul_1__ldbMul_1__ldcMul_1__batchType_0") in r.stdout
 
 
+def test_reference_benchmark_harness_compiles_unchanged():
+    """The reference's OWN benchmark executables (benchmark/portblas/main.cpp + blas3/{gemm,gemm_batched,
+    gemm_batched_strided,symm,trsm}.cpp with BLAS_VERIFY_BENCHMARK, half and complex as its CMake sets them) compile
+    UNCHANGED against include/ with a Google Benchmark stand-in and link against libpbx_gemm.so; without a GPU they parse
+    their command line (clara) and then refuse loudly when the queue is created -- there is no CPU fallback to time."""
+    if not Path("/root/reference/benchmark/portblas/main.cpp").exists():
+        pytest.skip("the reference tree is not present")
+    from portblas_b200 import build, build_host
+    build.build()
+    (ROOT / "build").mkdir(exist_ok=True)
+    built = build_host.build_reference_benchmarks()
+    assert sorted(p.name for p in built) == ["ref_bench_gemm", "ref_bench_gemm_batched", "ref_bench_gemm_batched_strided",
+                                             "ref_bench_symm", "ref_bench_trsm"]
+    r = subprocess.run([str(ROOT / "build" / "ref_bench_gemm"), "--help"], capture_output=True, text=True, timeout=60)
+    assert "--csv-param" in r.stdout
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([str(ROOT / "build" / "ref_bench_gemm")], capture_output=True, text=True, timeout=60)
+        assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
 @pytest.mark.gpu
 def test_own_cpp_caller_runs(handle):
     from portblas_b200 import build_host

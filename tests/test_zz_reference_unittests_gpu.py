@@ -3,8 +3,12 @@ against libpbx_gemm.so: test/unittest/blas3/blas3_gemm_test.cpp (float, double, 
 blas3_gemm_batched_test.cpp (strided + interleaved), blas3_gemm_tall_skinny_test.cpp, blas3_symm_test.cpp and
 blas3_trsm_test.cpp, each comparing with CBLAS through the reference's own verifier and tolerance.
 
-The binaries were first built after this round's GPU budget was spent, so this file has not run on a GPU yet: the tests
-are non-strict xfail until a box run confirms them (a pass shows as XPASS).  It sorts last on purpose.
+First box run (round 1, the last 20 s of the GPU budget, all binaries at once: profiles/r01/ref_unittests/):
+blas3_gemm_tall_skinny_test 320/320 and blas3_symm_test 488/488 (alloc_usm) PASSED; blas3_gemm_test 1189, blas3_gemm_batched_test
+854 and blas3_trsm_test 446 tests OK with none failed when the 20 s ran out (float, double, half->float, half->half reached;
+the complex suites were not).  The two complete suites are therefore plain tests; the three cut short stay non-strict xfail
+until a box run sees them end (a pass shows as XPASS).  The reference's benchmark executables (build/ref_bench_*) run here too,
+with the verification the reference builds them with by default.  The file sorts last on purpose.
 """
 from __future__ import annotations
 
@@ -28,14 +32,17 @@ SUITES = {
 }
 
 
-@pytest.mark.xfail(strict=False, reason="first GPU run of the reference's unit-test binaries happens after this round")
-@pytest.mark.parametrize("name", list(SUITES))
+COMPLETE_ON_THE_BOX = {"blas3_gemm_tall_skinny_test", "blas3_symm_test"}
+_unfinished = pytest.mark.xfail(strict=False, reason="ran clean on the box but was cut short by the round-1 GPU budget")
+
+
+@pytest.mark.parametrize("name", [n if n in COMPLETE_ON_THE_BOX else pytest.param(n, marks=_unfinished) for n in SUITES])
 def test_reference_unit_tests_pass_on_the_gpu(handle, name):
     exe = ROOT / "build" / f"ref_unittest_{name}"
     if not exe.exists():
         pytest.skip("reference unit tests were not prebuilt (needs /root/reference at build time)")
     flt, at_least = SUITES[name]
-    r = subprocess.run([str(exe), f"--gtest_filter={flt}"], capture_output=True, text=True, timeout=900)
+    r = subprocess.run([str(exe), f"--gtest_filter={flt}"], capture_output=True, text=True, timeout=420)
     tail = "\n".join(r.stdout.splitlines()[-15:])
     out_dir = ROOT / "gpurun_out" / "ref_unittests"
     out_dir.mkdir(parents=True, exist_ok=True)
@@ -45,3 +52,38 @@ def test_reference_unit_tests_pass_on_the_gpu(handle, name):
     n_ran = int(ran[-1].split()[1])
     assert "[  FAILED  ]" not in r.stdout, tail
     assert r.returncode == 0 and n_ran >= at_least, (r.returncode, n_ran, tail)
+
+
+# reference benchmark executable -> rows of its --csv-param file (benchmark/README.md: the column order per operator)
+BENCH_CSV = {
+    "gemm": "n,n,1024,1024,1024,1.5,0.5\nt,n,512,333,257,1,0\nn,t,63,1025,129,1,1\n",
+    "gemm_batched": "n,n,64,64,64,1,0,32,0\nt,n,33,65,17,1.5,0.5,7,0\nn,n,32,32,32,1,1,64,1\n",
+    "gemm_batched_strided": "n,n,128,128,128,1,0,16,2,2,2\nt,t,33,65,17,1.5,0.5,5,1,1,1\n",
+    "symm": "l,u,512,256,1,0\nr,l,127,255,1.5,0.5\n",
+    "trsm": "l,u,n,n,512,256,1\nr,l,t,u,127,255,2\n",
+}
+
+
+@_unfinished
+@pytest.mark.parametrize("name", list(BENCH_CSV))
+def test_reference_benchmark_harness_runs_and_verifies(handle, name, tmp_path):
+    """build/ref_bench_<name>: the reference's benchmark/portblas/blas3/<name>.cpp + main.cpp, unchanged, with
+    BLAS_VERIFY_BENCHMARK (each benchmark first checks its result against CBLAS and reports an error otherwise)."""
+    import json
+    exe = ROOT / "build" / f"ref_bench_{name}"
+    if not exe.exists():
+        pytest.skip("reference benchmarks were not prebuilt (needs /root/reference at build time)")
+    csv = tmp_path / "params.csv"
+    csv.write_text(BENCH_CSV[name])
+    out = tmp_path / "report.json"
+    r = subprocess.run([str(exe), "--csv-param", str(csv), "--benchmark_min_time=0.05", f"--benchmark_out={out}"],
+                       capture_output=True, text=True, timeout=420)
+    out_dir = ROOT / "gpurun_out" / "ref_unittests"
+    out_dir.mkdir(parents=True, exist_ok=True)
+    (out_dir / f"bench_{name}.log").write_text(r.stdout[-200000:] + "\n--- stderr ---\n" + r.stderr[-20000:])
+    assert "ERROR OCCURRED" not in r.stdout, r.stdout[-3000:]
+    assert r.returncode == 0, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
+    rep = json.loads(out.read_text())["benchmarks"]
+    assert len(rep) >= len(BENCH_CSV[name].splitlines()) * 2
+    for b in rep:
+        assert "error_occurred" not in b and b["real_time"] > 0 and b["n_fl_ops"] > 0, b
