@@ -1,0 +1,131 @@
+"""ctypes front for oracle/_ref/libportblas_ref_<backend>.so -- the REFERENCE's own GEMM on the host.  TEST INFRASTRUCTURE ONLY.
+
+What is inside the libraries: portBLAS's unmodified `blas::_gemm / _gemm_batched / _gemm_strided_batched`
+(include/interface/blas3_interface.h:86-123) with everything under them -- `_gemm_backend`
+(src/interface/gemm_interface.hpp:105-240), the backend heuristics (src/interface/blas3/backend/default.hpp or
+nvidia_gpu.hpp or intel_gpu.hpp with GEMM_TALL_SKINNY_SUPPORT -- one library per backend header), `Gemm_Launcher` (src/interface/gemm_launcher.hpp:39-64), `SB_Handle::execute`
+(src/sb_handle/portblas_handle.hpp:277-436), `execute_tree` (src/sb_handle/kernel_constructor.hpp:187-217) and the
+`Gemm<>` kernels (src/operations/blas3/gemm_*.hpp) -- compiled from /root/reference by oracle/ref_host_driver.cpp
+(`make -C oracle ref`) over a host stand-in for the SYCL runtime (oracle/sycl_host/sycl/sycl.hpp).  /root/reference only
+exists where the libraries are BUILT; the built .so files travel to the GPU box.
+
+Only tests/, __graft_entry__ (build + smoke check) and bench.py's reference / cpu_baseline leg import this module.
+"""
+from __future__ import annotations
+
+import ctypes
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+REF_DIR = HERE / "_ref"
+REFERENCE = Path("/root/reference")
+BACKENDS = ("default", "nvidia_gpu", "intel_gpu")
+_libs: dict = {}
+
+# suffix -> (numpy dtype of A/B, numpy dtype of C, ctypes type of alpha/beta)
+TYPES = {
+    "f32": (np.float32, np.float32, ctypes.c_float),
+    "f64": (np.float64, np.float64, ctypes.c_double),
+    "f16": (np.float16, np.float16, ctypes.c_float),
+    "f16f32": (np.float16, np.float32, ctypes.c_float),
+}
+
+
+def lib_path(backend: str) -> Path:
+    return REF_DIR / f"libportblas_ref_{backend}.so"
+
+
+def build(force: bool = False) -> list:
+    """Builds both libraries when the reference tree is present (idempotent); returns the libraries that exist."""
+    if (REFERENCE / "src" / "interface" / "gemm_interface.hpp").exists():
+        srcs = [HERE / "ref_host_driver.cpp", HERE / "sycl_host" / "sycl" / "sycl.hpp", HERE / "Makefile"]
+        newest = max(p.stat().st_mtime for p in srcs)
+        stale = force or any(not lib_path(b).exists() or lib_path(b).stat().st_mtime < newest for b in BACKENDS)
+        if stale:
+            r = subprocess.run(["make", "-C", str(HERE), "-j3", "-B", "ref"], capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("reference host build failed:\n" + r.stdout[-3000:] + r.stderr[-3000:])
+    return [lib_path(b) for b in BACKENDS if lib_path(b).exists()]
+
+
+def available(backend: str = "default") -> bool:
+    return lib_path(backend).exists()
+
+
+def lib(backend: str = "default") -> ctypes.CDLL:
+    if backend not in _libs:
+        if not available(backend):
+            raise FileNotFoundError(f"{lib_path(backend)} is not built (make -C oracle ref; needs /root/reference)")
+        L = ctypes.CDLL(str(lib_path(backend)))
+        L.ref_last_error.restype = ctypes.c_char_p
+        L.ref_backend.restype = ctypes.c_char_p
+        L.ref_compute_units.restype = ctypes.c_int
+        L.ref_set_fibers.argtypes = [ctypes.c_int]
+        c, i, vp = ctypes.c_char, ctypes.c_int, ctypes.c_void_p
+        for sfx, (_, _, ct) in TYPES.items():
+            getattr(L, f"ref_gemm_{sfx}").argtypes = [c, c, i, i, i, ct, vp, i, vp, i, ct, vp, i]
+            getattr(L, f"ref_gemm_batched_{sfx}").argtypes = [c, c, i, i, i, ct, vp, i, vp, i, ct, vp, i, i, i]
+            getattr(L, f"ref_gemm_strided_batched_{sfx}").argtypes = [c, c, i, i, i, ct, vp, i, i, vp, i, i, ct, vp, i, i, i]
+        assert L.ref_backend().decode() == backend
+        _libs[backend] = L
+    return _libs[backend]
+
+
+class ReferenceError_(Exception):
+    """std::invalid_argument (rc 1) or another exception (rc 2) thrown by the reference; the text is its what()."""
+
+
+def _check(L, rc):
+    if rc:
+        raise ReferenceError_(L.ref_last_error().decode())
+
+
+def _suffix(A: np.ndarray, C: np.ndarray) -> str:
+    for sfx, (ti, to, _) in TYPES.items():
+        if A.dtype == ti and C.dtype == to:
+            return sfx
+    raise TypeError(f"no reference instantiation for ({A.dtype}, {C.dtype})")
+
+
+def _b(ch: str) -> bytes:
+    return ch.encode()[:1]
+
+
+def gemm(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, *, backend="default") -> None:
+    """blas::_gemm on flat column-major numpy buffers, C in place."""
+    L = lib(backend)
+    sfx = _suffix(A, C)
+    _check(L, getattr(L, f"ref_gemm_{sfx}")(_b(ta), _b(tb), m, n, k, alpha, A.ctypes.data, lda, B.ctypes.data, ldb,
+                                            beta, C.ctypes.data, ldc))
+
+
+def gemm_batched(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, batch, interleaved=False, *,
+                 backend="default") -> None:
+    """blas::_gemm_batched (default strides = matrix footprints; batch_type strided 0 / interleaved 1)."""
+    L = lib(backend)
+    sfx = _suffix(A, C)
+    _check(L, getattr(L, f"ref_gemm_batched_{sfx}")(_b(ta), _b(tb), m, n, k, alpha, A.ctypes.data, lda, B.ctypes.data,
+                                                    ldb, beta, C.ctypes.data, ldc, batch, 1 if interleaved else 0))
+
+
+def gemm_strided_batched(ta, tb, m, n, k, alpha, A, lda, stride_a, B, ldb, stride_b, beta, C, ldc, stride_c, batch, *,
+                         backend="default") -> None:
+    """blas::_gemm_strided_batched."""
+    L = lib(backend)
+    sfx = _suffix(A, C)
+    _check(L, getattr(L, f"ref_gemm_strided_batched_{sfx}")(_b(ta), _b(tb), m, n, k, alpha, A.ctypes.data, lda, stride_a,
+                                                            B.ctypes.data, ldb, stride_b, beta, C.ctypes.data, ldc,
+                                                            stride_c, batch))
+
+
+def set_fibers(on: bool, backend: str = "default") -> None:
+    """False: work-items of barrier-free kernels run as plain loop iterations (every non-symm GEMM of the default backend
+    is barrier-free: default.hpp:52-147); a barrier reached in that mode aborts.  Used only for timing."""
+    lib(backend).ref_set_fibers(1 if on else 0)
+
+
+def compute_units(backend: str = "default") -> int:
+    return lib(backend).ref_compute_units()

@@ -1,0 +1,121 @@
+// ref_host_driver.cpp -- C entry points over the REFERENCE's own GEMM, compiled from its sources.  TEST INFRASTRUCTURE ONLY.
+//
+// Everything below `blas::_gemm` in this translation unit is portBLAS's unmodified code, included from where it lies
+// under /root/reference (include/ and src/; nothing is copied into this repository):
+//   include/interface/blas3_interface.h:86-123        blas::_gemm / _gemm_batched / _gemm_strided_batched
+//   src/interface/gemm_interface.hpp:105-240           _gemm_backend: alpha == 0 -> _scal / _scal_matrix, validation, dispatch
+//   src/interface/blas3/backend/{default,nvidia_gpu,intel_gpu}.hpp  tile heuristics (which one: -DNVIDIA_GPU / -DINTEL_GPU /
+//                                                      nothing, one library each: see Makefile)
+//   src/interface/gemm_launcher.hpp:39-64              views + make_gemm + SB_Handle::execute
+//   src/sb_handle/portblas_handle.hpp:277-436          nd_range sizing, tall-skinny GemmPartial + Reduction
+//   src/sb_handle/kernel_constructor.hpp:187-217       execute_tree (queue.submit / parallel_for)
+//   src/operations/blas3/gemm_*.hpp                    the kernels themselves
+// The only thing that is not the reference's is the SYCL runtime underneath: oracle/sycl_host/sycl/sycl.hpp, a host
+// stand-in that runs every work-group of the nd_range on the CPU (fibers for barriers, OpenMP over groups,
+// sycl::mad = fma).  So "reference outputs" here means: the reference's code on that executor.
+//
+// Used by tests/test_oracle_ref.py (pins oracle/gemm_oracle.c and the CUDA path against it) and by bench.py's
+// --impl reference / cpu_baseline leg (kind "reference").  The product never links or loads it.
+#include <sycl/sycl.hpp>
+
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "blas_meta.h"
+#include "container/sycl_iterator.h"
+#include "views/view.h"
+#include "views/view.hpp"
+#include "views/view_sycl.hpp"
+#include "sb_handle/portblas_handle.h"
+#include "sb_handle/kernel_constructor.hpp"
+#include "sb_handle/portblas_handle.hpp"
+#include "operations/blas_constants.hpp"
+#include "operations/blas1_trees.hpp"
+#include "operations/blas3_trees.hpp"
+#include "operations/extension/reduction.hpp"
+#include "interface/blas1_interface.hpp"
+#include "interface/gemm_launcher.hpp"
+#include "interface/gemm_interface.hpp"
+#include "interface/blas3_interface.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+blas::SB_Handle& handle() {
+  static sycl::queue q;
+  static blas::SB_Handle h(q);
+  return h;
+}
+
+template <typename F>
+int guarded(F&& f) {
+  try {
+    f();
+    g_last_error.clear();
+    return 0;
+  } catch (const std::invalid_argument& e) {  // gemm_interface.hpp:144-165
+    g_last_error = e.what();
+    return 1;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return 2;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ref_last_error() { return g_last_error.c_str(); }
+int ref_compute_units() { return (int)handle().get_num_compute_units(); }
+// which backend header this library was compiled with (src/interface/blas3/backend/backend.hpp:25-33): "default" (the CPU /
+// generic device), "nvidia_gpu", or "intel_gpu" (built with GEMM_TALL_SKINNY_SUPPORT: the only route to the reference's
+// tall-skinny GemmPartial + Reduction path, intel_gpu.hpp:67-140)
+const char* ref_backend() {
+#if defined(INTEL_GPU)
+  return "intel_gpu";
+#elif defined(NVIDIA_GPU)
+  return "nvidia_gpu";
+#else
+  return "default";
+#endif
+}
+// 0: work-items of barrier-free kernels run as plain loop iterations (timing); 1: always fibers (default)
+void ref_set_fibers(int on) { sycl::host_standin::kernels_use_barriers = (on != 0); }
+
+// TI: element type of A and B, TO: element type of C, alpha and beta (gemm.cpp.in:33-137: (float,float), (double,double),
+// (half,half), (half,float)).  Scalars cross the C boundary as TS (float for the half variants).
+#define REF_DEFINE(SUFFIX, TI, TO, TS)                                                                              \
+  int ref_gemm_##SUFFIX(char ta, char tb, int m, int n, int k, TS alpha, const TI* A, int lda, const TI* B,        \
+                        int ldb, TS beta, TO* C, int ldc) {                                                         \
+    return guarded([&] {                                                                                            \
+      blas::_gemm(handle(), ta, tb, m, n, k, TO(alpha), A, lda, B, ldb, TO(beta), C, ldc, {});                      \
+    });                                                                                                             \
+  }                                                                                                                 \
+  int ref_gemm_batched_##SUFFIX(char ta, char tb, int m, int n, int k, TS alpha, const TI* A, int lda,             \
+                                const TI* B, int ldb, TS beta, TO* C, int ldc, int batch, int batch_type) {         \
+    return guarded([&] {                                                                                            \
+      blas::_gemm_batched(handle(), ta, tb, m, n, k, TO(alpha), A, lda, B, ldb, TO(beta), C, ldc, batch,            \
+                          static_cast<blas::gemm_batch_type_t>(batch_type), {});                                    \
+    });                                                                                                             \
+  }                                                                                                                 \
+  int ref_gemm_strided_batched_##SUFFIX(char ta, char tb, int m, int n, int k, TS alpha, const TI* A, int lda,     \
+                                        int stride_a, const TI* B, int ldb, int stride_b, TS beta, TO* C, int ldc,  \
+                                        int stride_c, int batch) {                                                  \
+    return guarded([&] {                                                                                            \
+      blas::_gemm_strided_batched(handle(), ta, tb, m, n, k, TO(alpha), A, lda, stride_a, B, ldb, stride_b,         \
+                                  TO(beta), C, ldc, stride_c, batch, {});                                           \
+    });                                                                                                             \
+  }
+
+REF_DEFINE(f32, float, float, float)
+REF_DEFINE(f64, double, double, double)
+#ifdef BLAS_ENABLE_HALF
+REF_DEFINE(f16, sycl::half, sycl::half, float)
+REF_DEFINE(f16f32, sycl::half, float, float)
+#endif
+
+}  // extern "C"

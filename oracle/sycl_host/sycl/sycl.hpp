@@ -1,0 +1,609 @@
+// sycl/sycl.hpp -- a HOST stand-in for the SYCL 2020 names that portBLAS's GEMM kernels use.  TEST INFRASTRUCTURE ONLY.
+//
+// Why it exists: the reference (codeplaysoftware/portBLAS) is SYCL and this image has no SYCL compiler, so its GEMM could
+// only be restated (oracle/gemm_oracle.c).  With this header the reference's OWN kernel sources -- views, Gemm<> classes,
+// execute_tree -- compile UNCHANGED with g++ from where they lie under /root/reference (oracle/Makefile: _ref target;
+// nothing is copied) and run on the host: every work-group of the nd_range is executed, work-items in local-id order,
+// `nd_item::barrier` switches between the work-items of the group (ucontext fibers), local accessors are a per-group
+// scratch array.  Work-groups are spread over OpenMP threads (they are independent by the SYCL execution model).
+//
+// What it is not: a SYCL implementation.  Only the names the GEMM path touches exist, in the shape that path needs.
+// Numerics it fixes: sycl::mad(a, b, c) is the fused multiply-add std::fma (what a CPU OpenCL device emits on an FMA
+// machine, and the choice oracle/gemm_oracle.c makes); sycl::half is the compiler's _Float16.
+//
+// Only tests/, bench.py's reference / cpu_baseline leg and __graft_entry__ (build + smoke check) may use what is built
+// with this header; the product (libpbx_gemm.so) never does.
+#pragma once
+#include <ucontext.h>
+
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <exception>
+#include <functional>
+#include <iostream>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#define SYCL_LANGUAGE_VERSION 202001
+#define SYCL_HOST_STANDIN 1
+
+namespace sycl {
+
+using half = _Float16;
+
+enum class access_mode { read, write, read_write, discard_write, discard_read_write, atomic };
+enum class target { device, global_buffer = device, constant_buffer, local, host_buffer, host_task };
+namespace access {
+using mode = sycl::access_mode;
+using target = sycl::target;
+enum class placeholder { false_t, true_t };
+enum class address_space { global_space, local_space, constant_space, private_space, generic_space };
+enum class fence_space { local_space, global_space, global_and_local };
+enum class decorated { no, yes, legacy };
+}  // namespace access
+
+class exception : public std::runtime_error {
+ public:
+  explicit exception(const std::string& m) : std::runtime_error(m) {}
+};
+
+// ---------------------------------------------------------------- index space
+template <int D = 1>
+struct range {
+  static_assert(D == 1, "the GEMM path is one-dimensional");
+  size_t v = 0;
+  range() = default;
+  range(size_t a) : v(a) {}
+  size_t get(int) const { return v; }
+  size_t operator[](int) const { return v; }
+  size_t& operator[](int) { return v; }
+  size_t size() const { return v; }
+  friend range operator*(const range& a, const range& b) { return range(a.v * b.v); }
+  friend range operator/(const range& a, const range& b) { return range(a.v / b.v); }
+  friend range operator+(const range& a, const range& b) { return range(a.v + b.v); }
+  friend bool operator==(const range& a, const range& b) { return a.v == b.v; }
+};
+template <int D = 1>
+struct id {
+  static_assert(D == 1, "the GEMM path is one-dimensional");
+  size_t v = 0;
+  id() = default;
+  id(size_t a) : v(a) {}
+  size_t get(int) const { return v; }
+  size_t operator[](int) const { return v; }
+  operator size_t() const { return v; }
+};
+template <int D = 1>
+struct nd_range {
+  range<D> global, local;
+  nd_range(range<D> g, range<D> l) : global(g), local(l) {}
+  range<D> get_global_range() const { return global; }
+  range<D> get_local_range() const { return local; }
+  range<D> get_group_range() const { return range<D>(global.v / local.v); }
+};
+
+namespace detail {
+// The work-group executor sets this before it runs a work-item; barrier() calls it to yield to the next item.
+struct group_runner;
+inline thread_local group_runner* current_runner = nullptr;
+inline thread_local unsigned char* local_base = nullptr;  // this thread's work-group scratch (backs local accessors)
+inline void barrier_yield();
+}  // namespace detail
+
+namespace host_standin {
+// Set to false by a caller that KNOWS the next kernels never reach a barrier (the no-local GEMMs): their work-items then
+// run as plain loop iterations instead of fibers.  A barrier reached in that mode aborts loudly.
+inline bool kernels_use_barriers = true;
+}  // namespace host_standin
+
+// Declared so that the reference's non-GEMM headers parse; the GEMM path never executes them.
+[[noreturn]] inline void host_standin_unsupported(const char* what) {
+  std::cerr << "sycl host stand-in: " << what << " is not implemented (outside the GEMM path)\n";
+  std::abort();
+}
+struct sub_group {
+  id<1> get_local_id() const { return id<1>(0); }
+  size_t get_local_linear_id() const { return 0; }
+  range<1> get_local_range() const { return range<1>(1); }
+  size_t get_local_linear_range() const { return 1; }
+  id<1> get_group_id() const { return id<1>(0); }
+  size_t get_group_linear_id() const { return 0; }
+  range<1> get_group_range() const { return range<1>(1); }
+  range<1> get_max_local_range() const { return range<1>(1); }
+};
+template <int D = 1>
+struct group {
+  size_t id_ = 0;
+  size_t get_group_id(int = 0) const { return id_; }
+  size_t get_group_linear_id() const { return id_; }
+};
+template <typename T = void> struct plus { template <typename U> U operator()(const U& a, const U& b) const { return a + b; } };
+template <typename T = void> struct maximum { template <typename U> U operator()(const U& a, const U& b) const { return a < b ? b : a; } };
+template <typename T = void> struct minimum { template <typename U> U operator()(const U& a, const U& b) const { return b < a ? b : a; } };
+template <typename G, typename T, typename Op> T reduce_over_group(G, T, Op) { host_standin_unsupported("reduce_over_group"); }
+template <typename G, typename T> T group_broadcast(G, T, size_t = 0) { host_standin_unsupported("group_broadcast"); }
+template <typename G, typename T> T shift_group_left(G, T, size_t = 1) { host_standin_unsupported("shift_group_left"); }
+template <typename G, typename T> T shift_group_right(G, T, size_t = 1) { host_standin_unsupported("shift_group_right"); }
+template <typename G, typename T> T select_from_group(G, T, size_t) { host_standin_unsupported("select_from_group"); }
+enum class memory_order { relaxed, acquire, release, acq_rel, seq_cst };
+enum class memory_scope { work_item, sub_group, work_group, device, system };
+inline void atomic_fence(memory_order, memory_scope) {}
+template <typename T, memory_order O, memory_scope S,
+          access::address_space A = access::address_space::generic_space>
+class atomic_ref {
+ public:
+  explicit atomic_ref(T& r) : r_(r) {}
+  T load() const { return r_; }
+  void store(T v) const { r_ = v; }
+  T fetch_add(T v) const { host_standin_unsupported("atomic_ref::fetch_add"); }
+  T operator+=(T v) const { host_standin_unsupported("atomic_ref::operator+="); }
+  T operator++(int) const { host_standin_unsupported("atomic_ref::operator++"); }
+  T operator++() const { host_standin_unsupported("atomic_ref::operator++"); }
+  T operator--(int) const { host_standin_unsupported("atomic_ref::operator--"); }
+  T operator--() const { host_standin_unsupported("atomic_ref::operator--"); }
+  T fetch_max(T v) const { host_standin_unsupported("atomic_ref::fetch_max"); }
+  T fetch_min(T v) const { host_standin_unsupported("atomic_ref::fetch_min"); }
+  bool compare_exchange_strong(T&, T) const { host_standin_unsupported("atomic_ref::compare_exchange_strong"); }
+ private:
+  T& r_;
+};
+
+template <int D = 1>
+class nd_item {
+ public:
+  sub_group get_sub_group() const { return sub_group(); }
+  group<D> get_group() const { return group<D>{group_}; }
+  nd_item(size_t group, size_t local, size_t local_range, size_t group_range)
+      : group_(group), local_(local), local_range_(local_range), group_range_(group_range) {}
+  size_t get_local_id(int) const { return local_; }
+  id<D> get_local_id() const { return id<D>(local_); }
+  size_t get_local_linear_id() const { return local_; }
+  size_t get_group(int) const { return group_; }
+  size_t get_group_linear_id() const { return group_; }
+  size_t get_global_id(int) const { return group_ * local_range_ + local_; }
+  id<D> get_global_id() const { return id<D>(get_global_id(0)); }
+  size_t get_global_linear_id() const { return get_global_id(0); }
+  size_t get_local_range(int) const { return local_range_; }
+  range<D> get_local_range() const { return range<D>(local_range_); }
+  size_t get_group_range(int) const { return group_range_; }
+  range<D> get_group_range() const { return range<D>(group_range_); }
+  size_t get_global_range(int) const { return group_range_ * local_range_; }
+  range<D> get_global_range() const { return range<D>(get_global_range(0)); }
+  nd_range<D> get_nd_range() const { return nd_range<D>(get_global_range(), get_local_range()); }
+  void barrier(access::fence_space = access::fence_space::global_and_local) const { detail::barrier_yield(); }
+
+ private:
+  size_t group_, local_, local_range_, group_range_;
+};
+
+// ---------------------------------------------------------------- pointers and vectors
+template <typename T, access::address_space AS, access::decorated Dec = access::decorated::legacy>
+class multi_ptr {
+ public:
+  using element_type = T;
+  using pointer = T*;
+  multi_ptr() = default;
+  multi_ptr(T* p) : p_(p) {}
+  multi_ptr(std::nullptr_t) {}
+  template <typename U, access::address_space AS2, access::decorated D2,
+            typename = std::enable_if_t<std::is_convertible<U*, T*>::value>>
+  multi_ptr(const multi_ptr<U, AS2, D2>& o) : p_(o.get()) {}
+  T* get() const { return p_; }
+  T* get_raw() const { return p_; }
+  operator T*() const { return p_; }
+  T& operator*() const { return *p_; }
+  T* operator->() const { return p_; }
+  template <typename I, typename = std::enable_if_t<std::is_integral<I>::value>>
+  T& operator[](I i) const { return p_[i]; }
+  template <typename I, typename = std::enable_if_t<std::is_integral<I>::value>>
+  multi_ptr operator+(I i) const { return multi_ptr(p_ + i); }
+  template <typename I, typename = std::enable_if_t<std::is_integral<I>::value>>
+  multi_ptr operator-(I i) const { return multi_ptr(p_ - i); }
+  template <typename I, typename = std::enable_if_t<std::is_integral<I>::value>>
+  multi_ptr& operator+=(I i) { p_ += i; return *this; }
+  template <typename I, typename = std::enable_if_t<std::is_integral<I>::value>>
+  multi_ptr& operator-=(I i) { p_ -= i; return *this; }
+  multi_ptr& operator++() { ++p_; return *this; }
+  multi_ptr operator++(int) { multi_ptr t(*this); ++p_; return t; }
+
+ private:
+  T* p_ = nullptr;
+};
+template <typename T, access::decorated Dec = access::decorated::legacy>
+using global_ptr = multi_ptr<T, access::address_space::global_space, Dec>;
+template <typename T, access::decorated Dec = access::decorated::legacy>
+using local_ptr = multi_ptr<T, access::address_space::local_space, Dec>;
+template <typename T, access::decorated Dec = access::decorated::legacy>
+using private_ptr = multi_ptr<T, access::address_space::private_space, Dec>;
+
+template <typename T, int N>
+struct vec {
+  using element_type = T;
+  T s[N];
+  vec() { for (int i = 0; i < N; ++i) s[i] = T{}; }
+  vec(const T& a) { for (int i = 0; i < N; ++i) s[i] = a; }
+  template <typename... U, typename = std::enable_if_t<(sizeof...(U) == N) && (N > 1)>>
+  vec(U... a) : s{static_cast<T>(a)...} {}
+  static constexpr int size() { return N; }
+  T& operator[](int i) { return s[i]; }
+  const T& operator[](int i) const { return s[i]; }
+  template <access::address_space AS, access::decorated Dec>
+  void load(size_t off, multi_ptr<const T, AS, Dec> p) {
+    std::memcpy(s, p.get() + off * N, sizeof(T) * N);
+  }
+  template <access::address_space AS, access::decorated Dec>
+  void load(size_t off, multi_ptr<T, AS, Dec> p) {
+    std::memcpy(s, p.get() + off * N, sizeof(T) * N);
+  }
+  template <access::address_space AS, access::decorated Dec>
+  void store(size_t off, multi_ptr<T, AS, Dec> p) const {
+    std::memcpy(p.get() + off * N, s, sizeof(T) * N);
+  }
+#define SYCL_HOST_VEC_OP(OP)                                                  \
+  friend vec operator OP(const vec& a, const vec& b) {                        \
+    vec r;                                                                    \
+    for (int i = 0; i < N; ++i) r.s[i] = a.s[i] OP b.s[i];                    \
+    return r;                                                                 \
+  }                                                                           \
+  friend vec operator OP(const vec& a, const T& b) { return a OP vec(b); }    \
+  friend vec operator OP(const T& a, const vec& b) { return vec(a) OP b; }    \
+  vec& operator OP##=(const vec& b) { return *this = *this OP b; }            \
+  vec& operator OP##=(const T& b) { return *this = *this OP vec(b); }
+  SYCL_HOST_VEC_OP(+)
+  SYCL_HOST_VEC_OP(-)
+  SYCL_HOST_VEC_OP(*)
+  SYCL_HOST_VEC_OP(/)
+#undef SYCL_HOST_VEC_OP
+};
+
+inline float mad(float a, float b, float c) { return std::fma(a, b, c); }
+inline double mad(double a, double b, double c) { return std::fma(a, b, c); }
+inline half mad(half a, half b, half c) { return static_cast<half>(std::fma(float(a), float(b), float(c))); }
+template <typename T, int N>
+inline vec<T, N> mad(const vec<T, N>& a, const vec<T, N>& b, const vec<T, N>& c) {
+  vec<T, N> r;
+  for (int i = 0; i < N; ++i) r.s[i] = mad(a.s[i], b.s[i], c.s[i]);
+  return r;
+}
+inline float fma(float a, float b, float c) { return std::fma(a, b, c); }
+inline double fma(double a, double b, double c) { return std::fma(a, b, c); }
+template <typename T> inline T fabs(T a) { return std::fabs(a); }
+template <typename T> inline T abs(T a) { return a < T(0) ? -a : a; }
+template <typename T> inline T sqrt(T a) { return std::sqrt(a); }
+template <typename T> inline T sign(T a) { return a > T(0) ? T(1) : (a < T(0) ? T(-1) : a); }
+template <typename T> inline T hypot(T a, T b) { return std::hypot(a, b); }
+template <typename T> inline T min(T a, T b) { return b < a ? b : a; }
+template <typename T> inline T max(T a, T b) { return a < b ? b : a; }
+
+// ---------------------------------------------------------------- devices, events, queue
+namespace info {
+namespace device {
+struct name { using return_type = std::string; };
+struct vendor { using return_type = std::string; };
+struct max_compute_units { using return_type = unsigned; };
+struct max_work_group_size { using return_type = size_t; };
+struct local_mem_size { using return_type = size_t; };
+struct local_mem_type { using return_type = int; };
+struct sub_group_sizes { using return_type = std::vector<size_t>; };
+struct device_type { using return_type = int; };
+}  // namespace device
+enum class device_type { cpu, gpu, accelerator, host, all };
+namespace local_mem_type_ns {
+enum type : int { none = 0, local = 1, global = 2 };
+}
+struct local_mem_type {  // usable both as sycl::info::local_mem_type::local and as a value compared with an int
+  static constexpr int none = 0, local = 1, global = 2;
+};
+namespace event_profiling {
+struct command_start { using return_type = uint64_t; };
+struct command_end { using return_type = uint64_t; };
+}  // namespace event_profiling
+}  // namespace info
+
+int host_compute_units();  // OpenMP threads available to the executor
+
+class device {
+ public:
+  template <typename P>
+  typename P::return_type get_info() const {
+    if constexpr (std::is_same_v<P, info::device::name>) return "host stand-in (oracle/sycl_host)";
+    else if constexpr (std::is_same_v<P, info::device::vendor>) return "none";
+    else if constexpr (std::is_same_v<P, info::device::max_compute_units>) return (unsigned)host_compute_units();
+    else if constexpr (std::is_same_v<P, info::device::max_work_group_size>) return (size_t)1024;
+    else if constexpr (std::is_same_v<P, info::device::local_mem_size>) return (size_t)(64 * 1024);
+    else if constexpr (std::is_same_v<P, info::device::local_mem_type>) return info::local_mem_type::local;
+    else if constexpr (std::is_same_v<P, info::device::sub_group_sizes>) return std::vector<size_t>{1};
+    else return typename P::return_type{};
+  }
+  bool is_cpu() const { return true; }
+  bool is_gpu() const { return false; }
+};
+
+class event {
+ public:
+  void wait() const {}
+  void wait_and_throw() const {}
+  static void wait(const std::vector<event>&) {}  // everything in this stand-in has completed when submit returns
+  template <typename P>
+  uint64_t get_profiling_info() const { return 0; }
+};
+
+template <typename T, int D = 1, typename Alloc = void>
+class buffer {
+ public:
+  using value_type = T;
+  buffer() = default;
+  explicit buffer(range<D> r) : n_(r.size()), own_(new std::remove_const_t<T>[r.size() ? r.size() : 1](), std::default_delete<std::remove_const_t<T>[]>()), p_(own_.get()) {}
+  buffer(T* host, range<D> r) : n_(r.size()), p_(const_cast<std::remove_const_t<T>*>(host)) {}
+  size_t size() const { return n_; }
+  size_t get_count() const { return n_; }
+  size_t byte_size() const { return n_ * sizeof(T); }
+  range<D> get_range() const { return range<D>(n_); }
+  std::remove_const_t<T>* host_data() const { return p_; }
+  template <typename U, int D2 = D>
+  buffer<U, D2> reinterpret(range<D2> r) const {
+    buffer<U, D2> b;
+    b.adopt(reinterpret_cast<std::remove_const_t<U>*>(p_), r.size(), own_);
+    return b;
+  }
+  void adopt(std::remove_const_t<T>* p, size_t n, std::shared_ptr<void> keep) { p_ = p; n_ = n; keep_ = std::move(keep); }
+
+ private:
+  size_t n_ = 0;
+  std::shared_ptr<std::remove_const_t<T>> own_;
+  std::shared_ptr<void> keep_;
+  std::remove_const_t<T>* p_ = nullptr;
+};
+
+class handler;
+
+template <typename T, int D = 1, access_mode M = access_mode::read_write, target Tg = target::device,
+          access::placeholder P = access::placeholder::false_t>
+class accessor {
+ public:
+  using value_type = T;
+  accessor() = default;
+  template <typename U>
+  accessor(buffer<U, D> b, handler&, range<D> r, id<D> off = id<D>(0)) : p_(b.host_data() + off.v), n_(r.size()) {}
+  template <typename U>
+  accessor(buffer<U, D> b, range<D> r, id<D> off = id<D>(0)) : p_(b.host_data() + off.v), n_(r.size()) {}
+  template <typename U>
+  accessor(buffer<U, D> b, handler&) : p_(b.host_data()), n_(b.size()) {}
+  template <typename U>
+  explicit accessor(buffer<U, D> b) : p_(b.host_data()), n_(b.size()) {}
+  size_t size() const { return n_; }
+  size_t get_size() const { return n_ * sizeof(T); }
+  size_t get_count() const { return n_; }
+  global_ptr<T> get_pointer() const { return global_ptr<T>(p_); }
+  template <access::decorated Dec = access::decorated::legacy>
+  global_ptr<T, Dec> get_multi_ptr() const { return global_ptr<T, Dec>(p_); }
+  T& operator[](size_t i) const { return p_[i]; }
+  id<D> get_offset() const { return id<D>(0); }
+
+ private:
+  T* p_ = nullptr;
+  size_t n_ = 0;
+};
+
+template <typename T, int D = 1>
+class local_accessor {
+ public:
+  using value_type = T;
+  local_accessor() = default;
+  local_accessor(range<D> r, handler& h);
+  size_t size() const { return n_; }
+  // the base is the EXECUTING thread's scratch, looked up at use time (the accessor is created on the submitting thread)
+  T* data() const { return reinterpret_cast<T*>(detail::local_base + offset_); }
+  local_ptr<T> get_pointer() const { return local_ptr<T>(data()); }
+  template <access::decorated Dec = access::decorated::legacy>
+  local_ptr<T, Dec> get_multi_ptr() const { return local_ptr<T, Dec>(data()); }
+  T& operator[](size_t i) const { return data()[i]; }
+
+ private:
+  size_t n_ = 0, offset_ = 0;
+};
+
+// One work-group at a time, work-items as fibers so that nd_item::barrier can switch between them.
+namespace detail {
+struct group_runner {
+  static constexpr size_t kStack = 64 * 1024;
+  struct fiber {
+    ucontext_t ctx;
+    std::unique_ptr<unsigned char[]> stack;
+    bool done = true;
+  };
+  std::vector<fiber> fibers;
+  ucontext_t scheduler;
+  size_t running = 0;
+  std::function<void(size_t)> body;  // body(local id)
+  bool needs_fibers = true;
+
+  static void trampoline() {
+    group_runner* r = current_runner;
+    r->body(r->running);
+    r->fibers[r->running].done = true;
+    swapcontext(&r->fibers[r->running].ctx, &r->scheduler);
+  }
+  void yield() {
+    if (!needs_fibers) {
+      std::cerr << "sycl host stand-in: barrier reached in a kernel launched with kernels_use_barriers = false\n";
+      std::abort();
+    }
+    swapcontext(&fibers[running].ctx, &scheduler);
+  }
+  void run_group(size_t local_size) {
+    current_runner = this;
+    if (!needs_fibers) {
+      for (size_t l = 0; l < local_size; ++l) body(l);
+      return;
+    }
+    if (fibers.size() < local_size) fibers.resize(local_size);
+    for (size_t l = 0; l < local_size; ++l) {
+      fiber& f = fibers[l];
+      if (!f.stack) f.stack.reset(new unsigned char[kStack]);
+      getcontext(&f.ctx);
+      f.ctx.uc_stack.ss_sp = f.stack.get();
+      f.ctx.uc_stack.ss_size = kStack;
+      f.ctx.uc_link = &scheduler;
+      makecontext(&f.ctx, (void (*)())trampoline, 0);
+      f.done = false;
+    }
+    size_t left = local_size;
+    while (left) {  // round robin: every item runs to its next barrier (or its end) in local-id order
+      for (size_t l = 0; l < local_size; ++l) {
+        if (fibers[l].done) continue;
+        running = l;
+        swapcontext(&scheduler, &fibers[l].ctx);
+        if (fibers[l].done) --left;
+      }
+    }
+  }
+};
+inline void barrier_yield() {
+  if (current_runner) current_runner->yield();
+}
+}  // namespace detail
+
+class handler {
+ public:
+  template <typename... A>
+  void depends_on(A&&...) {}
+  template <typename A>
+  void require(A&&) {}
+  size_t reserve_local(size_t bytes) {
+    const size_t at = (local_bytes_ + 63) & ~size_t(63);
+    local_bytes_ = at + bytes;
+    return at;
+  }
+
+  // Executes the whole nd_range now (see host_standin::kernels_use_barriers).
+  template <typename K>
+  void parallel_for(nd_range<1> r, K kernel) { run(r, kernel, host_standin::kernels_use_barriers); }
+  template <typename Name, typename K>
+  void parallel_for(nd_range<1> r, K kernel) { run(r, kernel, host_standin::kernels_use_barriers); }
+  template <typename T, typename Acc>
+  void copy(const T* src, Acc dst) { std::memcpy(&dst[0], src, dst.size() * sizeof(T)); }
+  template <typename Acc, typename T, typename = std::enable_if_t<!std::is_pointer<Acc>::value>>
+  void copy(Acc src, T* dst) { std::memcpy(dst, &src[0], src.size() * sizeof(T)); }
+  template <typename Acc, typename T, typename = std::enable_if_t<!std::is_pointer<Acc>::value>>
+  void fill(Acc dst, const T& v) { for (size_t i = 0; i < dst.size(); ++i) dst[i] = v; }
+  template <typename T>
+  void fill(T* dst, const T& v, size_t n) { std::fill(dst, dst + n, v); }
+  void memcpy(void* dst, const void* src, size_t n) { std::memcpy(dst, src, n); }
+  template <typename K>
+  void single_task(K kernel) { kernel(); }
+  template <typename K>
+  void host_task(K kernel) { kernel(); }
+
+ private:
+  template <typename K>
+  void run(nd_range<1> r, const K& kernel, bool fibers);
+  size_t local_bytes_ = 0;
+};
+
+template <typename T, int D>
+local_accessor<T, D>::local_accessor(range<D> r, handler& h)
+    : n_(r.size()), offset_(h.reserve_local(r.size() * sizeof(T))) {}
+
+}  // namespace sycl
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace sycl {
+
+inline int host_compute_units() {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+template <typename K>
+void handler::run(nd_range<1> r, const K& kernel, bool fibers) {
+  const size_t local = r.get_local_range()[0];
+  const size_t groups = r.get_group_range()[0];
+  const size_t local_bytes = local_bytes_ + 64;
+  std::exception_ptr err;
+#pragma omp parallel
+  {
+    static thread_local detail::group_runner runner;
+    static thread_local std::vector<unsigned char> scratch;
+    if (scratch.size() < local_bytes) scratch.resize(local_bytes);
+    detail::local_base = scratch.data();
+    runner.needs_fibers = fibers;
+#pragma omp for schedule(dynamic, 1)
+    for (size_t g = 0; g < groups; ++g) {
+      try {
+        // every work-item gets its OWN copy of the kernel function object, as on a device: portBLAS's kernels keep
+        // per-item state in it (views set their pointer in eval; gemm_interleaved.hpp counts its k_ member down)
+        runner.body = [&kernel, g, local, groups](size_t l) {
+          K k = kernel;
+          k(nd_item<1>(g, l, local, groups));
+        };
+        runner.run_group(local);
+      } catch (...) {
+#pragma omp critical
+        err = std::current_exception();
+      }
+    }
+    detail::current_runner = nullptr;
+  }
+  if (err) std::rethrow_exception(err);
+}
+
+struct default_selector {};
+inline constexpr default_selector default_selector_v{};
+struct cpu_selector {};
+inline constexpr cpu_selector cpu_selector_v{};
+namespace property {
+namespace queue {
+struct enable_profiling {};
+struct in_order {};
+}  // namespace queue
+}  // namespace property
+
+class context {};
+
+class queue {
+ public:
+  queue() = default;
+  template <typename... A>
+  explicit queue(A&&...) {}
+  template <typename F>
+  event submit(F&& cgf) {
+    handler h;
+    cgf(h);
+    return event();
+  }
+  void wait() {}
+  void wait_and_throw() {}
+  device get_device() const { return device(); }
+  context get_context() const { return context(); }
+  event memcpy(void* dst, const void* src, size_t n) { std::memcpy(dst, src, n); return event(); }
+  template <typename T>
+  event fill(T* p, const T& v, size_t n) { std::fill(p, p + n, v); return event(); }
+};
+
+namespace usm {
+enum class alloc { host, device, shared, unknown };
+}
+inline usm::alloc get_pointer_type(const void*, const context&) { return usm::alloc::device; }
+template <typename T> T* malloc_device(size_t n, const queue&) { return static_cast<T*>(std::malloc(n * sizeof(T))); }
+template <typename T> T* malloc_shared(size_t n, const queue&) { return static_cast<T*>(std::malloc(n * sizeof(T))); }
+template <typename T> T* malloc_host(size_t n, const queue&) { return static_cast<T*>(std::malloc(n * sizeof(T))); }
+inline void free(void* p, const queue&) { std::free(p); }
+inline void free(void* p, const context&) { std::free(p); }
+
+}  // namespace sycl
