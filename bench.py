@@ -150,22 +150,42 @@ class ClockSampler:
                     reasons=sorted(reasons))
 
 
+def _cpu_gemm():
+    """The CPU GEMM both CPU legs time: the REFERENCE's own code when oracle/_ref was built (portBLAS's blas::_gemm,
+    default backend, compiled from its sources over a host stand-in for the SYCL runtime: oracle/ref_host_driver.cpp;
+    work-items of its barrier-free kernels run as plain loop iterations, work-groups over OpenMP threads), else the C
+    port of the kernel that backend picks (oracle/gemm_oracle.c -- bit-identical results, tests/test_oracle_ref.py).
+    Returns (fn(ms, n, k, a, b, c), kind, cores, label)."""
+    from oracle import oracle, ref_host
+    if ref_host.available("default"):
+        ref_host.set_fibers(False)
+
+        def fn(ms, n, k, a, b, c):
+            ref_host.gemm("n", "n", ms, n, k, 1.0, a, ms, b, k, 0.0, c, ms)
+        return fn, "reference", ref_host.compute_units("default"), (
+            "portBLAS's own blas::_gemm (default backend, compiled from the reference's sources over a host "
+            "stand-in for the SYCL runtime, oracle/_ref), OpenMP over work-groups")
+
+    def fn(ms, n, k, a, b, c):
+        oracle.gemm_default_cpu(False, False, ms, n, k, 1.0, a, ms, b, k, 0.0, c, ms)
+    return fn, "port", oracle.num_threads(), "the restated DEFAULT-backend kernel (oracle/gemm_oracle.c, OpenMP)"
+
+
 def cpu_sample(w, target_s=12.0):
-    """Bounded CPU sample of the same workload: the restated DEFAULT-backend portBLAS kernel
-    (oracle port, OpenMP over work-groups) on the first ``ms`` rows of C with full N and K."""
+    """Bounded CPU sample of the same workload on the first ``ms`` rows of C with full N and K (see _cpu_gemm)."""
     import numpy as np
     from oracle import oracle
     npdt = np.float64 if w["dt"] == "f64" else np.float32
     n, k = min(w["n"], 8192), min(w["k"], 8192)
     rng = np.random.default_rng(12345)
-    cores = oracle.num_threads()
+    gemm, kind, cores, label = _cpu_gemm()
 
     def run(ms):
         a = oracle.random_uniform(rng, ms * k, npdt)
         b = oracle.random_uniform(rng, k * n, npdt)
         c = np.zeros(ms * n, dtype=npdt)
         t0 = time.perf_counter()
-        oracle.gemm_default_cpu(False, False, ms, n, k, 1.0, a, ms, b, k, 0.0, c, ms)
+        gemm(ms, n, k, a, b, c)
         dt = time.perf_counter() - t0
         t1 = time.perf_counter()
         cc = a.reshape(k, ms).T @ b.reshape(n, k).T  # OpenBLAS (the reference tests' CBLAS oracle)
@@ -173,22 +193,20 @@ def cpu_sample(w, target_s=12.0):
         del cc
         return dt, dt_blas
 
-    probe_ms = 16
+    probe_ms = 64
     dt, _ = run(probe_ms)
     rate = 2.0 * probe_ms * n * k / dt
-    ms = int(min(w["m"], max(16, (target_s * rate / (2.0 * n * k)) // 16 * 16)))
+    ms = int(min(w["m"], max(64, (target_s * rate / (2.0 * n * k)) // 16 * 16)))
     dt, dt_blas = run(ms)
     fl = 2.0 * ms * n * k
-    return dict(value=round(fl / dt / 1e12, 5), unit="TFLOP/s", cores=cores, kind="port",
-                sample=f"first {ms} rows of C x N={n} x K={k} ({fl / 1e9:.1f} GFLOP, {dt:.1f} s) with the restated "
-                       f"DEFAULT-backend kernel (oracle/gemm_oracle.c, OpenMP)",
+    return dict(value=round(fl / dt / 1e12, 5), unit="TFLOP/s", cores=cores, kind=kind,
+                sample=f"first {ms} rows of C x N={n} x K={k} ({fl / 1e9:.1f} GFLOP, {dt:.1f} s) with {label}",
                 cblas_tflops=round(fl / dt_blas / 1e12, 5))
 
 
 def run_reference(args, w, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path.  portBLAS is SYCL and
-    cannot be built here, so this times the oracle port (restated DEFAULT-backend kernel) with all
-    host threads, each step a bounded sample of the workload."""
+    """--impl reference: the reference's own CPU implementation of the path with all host threads, each step a bounded
+    sample of the workload (see _cpu_gemm for what runs)."""
     if rank != 0:
         return
     import numpy as np
@@ -197,14 +215,15 @@ def run_reference(args, w, rank, world):
     n, k = min(w["n"], 4096), min(w["k"], 4096)
     ms = 256
     rng = np.random.default_rng(12345)
+    gemm, kind, cores, label = _cpu_gemm()
     a = oracle.random_uniform(rng, ms * k, npdt)
     b = oracle.random_uniform(rng, k * n, npdt)
     c = np.zeros(ms * n, dtype=npdt)
     for _ in range(args.warmup):
-        oracle.gemm_default_cpu(False, False, ms, n, k, 1.0, a, ms, b, k, 0.0, c, ms)
+        gemm(ms, n, k, a, b, c)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle.gemm_default_cpu(False, False, ms, n, k, 1.0, a, ms, b, k, 0.0, c, ms)
+        gemm(ms, n, k, a, b, c)
     dt = (time.perf_counter() - t0) / args.steps
     fl = 2.0 * ms * n * k
     val = fl / dt / 1e12
@@ -213,12 +232,11 @@ def run_reference(args, w, rank, world):
                 steps=args.steps, warmup=args.warmup, ms_per_step=round(dt * 1e3, 3), higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype=w["dt"], data="synthetic U(-2,5) seed 12345",
                 config=dict(workload=w["desc"], sample=sample),
-                cpu_baseline=dict(value=round(val, 5), unit="TFLOP/s", cores=oracle.num_threads(), kind="port",
-                                  sample=sample),
+                cpu_baseline=dict(value=round(val, 5), unit="TFLOP/s", cores=cores, kind=kind, sample=sample),
                 e2e=dict(value=round(val, 5), unit="TFLOP/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0,
-                note="portBLAS needs a SYCL compiler (absent): reference arm = oracle port of its DEFAULT-backend "
-                     "CPU kernel, all host threads")
+                note=f"reference arm = {label}; portBLAS needs a SYCL compiler (absent in this image), so its kernels run "
+                     "on a host executor rather than on a SYCL CPU device")
     print(json.dumps(line), flush=True)
 
 

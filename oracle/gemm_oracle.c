@@ -4,14 +4,16 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
  * may load this.  The product (libpbx_gemm.so) never links or calls it.
  *
- * PARITY STATUS: the reference (codeplaysoftware/portBLAS @ 6cf5e58) is SYCL and cannot be
- * compiled in this image (no SYCL compiler), and it ships no golden vectors: its own tests
- * compare against a system CBLAS at run time on random inputs
- * (test/unittest/blas3/blas3_gemm_common.hpp:164-169,223-225).  This restatement is therefore
- * "parity unpinned" against reference OUTPUTS; it is pinned instead (tests/test_oracle.py)
- * against the oracle the reference's tests use -- CBLAS (OpenBLAS 0.3.30 via numpy) -- on the
- * reference's own parameter grids, input distribution U(-2,5) and tolerance function
- * (common/include/common/float_comparison.hpp:163-188).
+ * PARITY STATUS: PINNED against outputs of the reference itself.  The reference (codeplaysoftware/portBLAS @ 6cf5e58)
+ * is SYCL and this image has no SYCL compiler, but its GEMM path is header-only: `make ref` compiles it unchanged from
+ * /root/reference over a host stand-in for the SYCL runtime (ref_host_driver.cpp, sycl_host/sycl/sycl.hpp) into
+ * oracle/_ref/, and tests/test_oracle_ref.py checks that the "gemm_local ordering" below and the DEFAULT-backend kernel
+ * reproduce it BIT FOR BIT on the reference's grids (single, strided-batched, interleaved; default and NVIDIA backend
+ * heuristics), the front-end rules included; committed outputs of it (tests/golden/ref_host_golden.npz) keep the pin
+ * where oracle/_ref is absent.  The reference ships no golden vectors of its own (its tests compare against a system
+ * CBLAS at run time on random inputs, test/unittest/blas3/blas3_gemm_common.hpp:164-169,223-225), so this file is also
+ * pinned (tests/test_oracle.py) against that CBLAS -- OpenBLAS 0.3.30 via numpy -- on the reference's parameter grids,
+ * input distribution U(-2,5) and tolerance function (common/include/common/float_comparison.hpp:163-188).
  *
  * What is restated, with the reference lines each function follows:
  *   oracle_gemm_ref_*     naive kernel            src/operations/blas3/gemm_ref.hpp:204-260
