@@ -1,7 +1,8 @@
 """ctypes front for oracle/_ref/libportblas_ref_<backend>.so -- the REFERENCE's own GEMM on the host.  TEST INFRASTRUCTURE ONLY.
 
-What is inside the libraries: portBLAS's unmodified `blas::_gemm / _gemm_batched / _gemm_strided_batched`
-(include/interface/blas3_interface.h:86-123) with everything under them -- `_gemm_backend`
+What is inside the libraries: portBLAS's unmodified `blas::_gemm / _gemm_batched / _gemm_strided_batched` and the two
+callers of that path, `blas::_symm` and `blas::_trsm` (include/interface/blas3_interface.h:86-146) with everything under
+them -- `_gemm_backend`
 (src/interface/gemm_interface.hpp:105-240), the backend heuristics (src/interface/blas3/backend/default.hpp or
 nvidia_gpu.hpp or intel_gpu.hpp with GEMM_TALL_SKINNY_SUPPORT -- one library per backend header), `Gemm_Launcher` (src/interface/gemm_launcher.hpp:39-64), `SB_Handle::execute`
 (src/sb_handle/portblas_handle.hpp:277-436), `execute_tree` (src/sb_handle/kernel_constructor.hpp:187-217) and the
@@ -69,6 +70,9 @@ def lib(backend: str = "default") -> ctypes.CDLL:
             getattr(L, f"ref_gemm_{sfx}").argtypes = [c, c, i, i, i, ct, vp, i, vp, i, ct, vp, i]
             getattr(L, f"ref_gemm_batched_{sfx}").argtypes = [c, c, i, i, i, ct, vp, i, vp, i, ct, vp, i, i, i]
             getattr(L, f"ref_gemm_strided_batched_{sfx}").argtypes = [c, c, i, i, i, ct, vp, i, i, vp, i, i, ct, vp, i, i, i]
+        for sfx, ct in (("f32", ctypes.c_float), ("f64", ctypes.c_double)):
+            getattr(L, f"ref_symm_{sfx}").argtypes = [c, c, i, i, ct, vp, i, vp, i, ct, vp, i]
+            getattr(L, f"ref_trsm_{sfx}").argtypes = [c, c, c, c, i, i, ct, vp, i, vp, i]
         assert L.ref_backend().decode() == backend
         _libs[backend] = L
     return _libs[backend]
@@ -119,6 +123,22 @@ def gemm_strided_batched(ta, tb, m, n, k, alpha, A, lda, stride_a, B, ldb, strid
     _check(L, getattr(L, f"ref_gemm_strided_batched_{sfx}")(_b(ta), _b(tb), m, n, k, alpha, A.ctypes.data, lda, stride_a,
                                                             B.ctypes.data, ldb, stride_b, beta, C.ctypes.data, ldc,
                                                             stride_c, batch))
+
+
+def symm(side, uplo, m, n, alpha, A, lda, B, ldb, beta, C, ldc, *, backend="default") -> None:
+    """blas::_symm (src/interface/symm_interface.hpp:35-71), C in place."""
+    L = lib(backend)
+    sfx = _suffix(A, C)
+    _check(L, getattr(L, f"ref_symm_{sfx}")(_b(side), _b(uplo), m, n, alpha, A.ctypes.data, lda, B.ctypes.data, ldb, beta,
+                                            C.ctypes.data, ldc))
+
+
+def trsm(side, uplo, trans, diag, m, n, alpha, A, lda, B, ldb, *, backend="default") -> None:
+    """blas::_trsm (src/interface/trsm_interface.hpp:150-387), B in place."""
+    L = lib(backend)
+    sfx = _suffix(A, B)
+    _check(L, getattr(L, f"ref_trsm_{sfx}")(_b(side), _b(uplo), _b(trans), _b(diag), m, n, alpha, A.ctypes.data, lda,
+                                            B.ctypes.data, ldb))
 
 
 def set_fibers(on: bool, backend: str = "default") -> None:

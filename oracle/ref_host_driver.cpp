@@ -7,6 +7,7 @@
 //   src/interface/blas3/backend/{default,nvidia_gpu,intel_gpu}.hpp  tile heuristics (which one: -DNVIDIA_GPU / -DINTEL_GPU /
 //                                                      nothing, one library each: see Makefile)
 //   src/interface/gemm_launcher.hpp:39-64              views + make_gemm + SB_Handle::execute
+//   src/interface/symm_interface.hpp:35-71, trsm_interface.hpp:150-387  the two callers of the path
 //   src/sb_handle/portblas_handle.hpp:277-436          nd_range sizing, tall-skinny GemmPartial + Reduction
 //   src/sb_handle/kernel_constructor.hpp:187-217       execute_tree (queue.submit / parallel_for)
 //   src/operations/blas3/gemm_*.hpp                    the kernels themselves
@@ -38,6 +39,8 @@
 #include "interface/blas1_interface.hpp"
 #include "interface/gemm_launcher.hpp"
 #include "interface/gemm_interface.hpp"
+#include "interface/symm_interface.hpp"
+#include "interface/trsm_interface.hpp"
 #include "interface/blas3_interface.h"
 
 namespace {
@@ -111,8 +114,21 @@ void ref_set_fibers(int on) { sycl::host_standin::kernels_use_barriers = (on != 
     });                                                                                                             \
   }
 
+// blas::_symm and blas::_trsm (float and double only, as in the reference: symm.cpp.in / trsm.cpp.in)
+#define REF_DEFINE_EXT(SUFFIX, T)                                                                                   \
+  int ref_symm_##SUFFIX(char side, char uplo, int m, int n, T alpha, const T* A, int lda, const T* B, int ldb,     \
+                        T beta, T* C, int ldc) {                                                                    \
+    return guarded([&] { blas::_symm(handle(), side, uplo, m, n, alpha, A, lda, B, ldb, beta, C, ldc, {}); });     \
+  }                                                                                                                 \
+  int ref_trsm_##SUFFIX(char side, char uplo, char trans, char diag, int m, int n, T alpha, const T* A, int lda,   \
+                        T* B, int ldb) {                                                                            \
+    return guarded([&] { blas::_trsm(handle(), side, uplo, trans, diag, m, n, alpha, A, lda, B, ldb, {}); });      \
+  }
+
 REF_DEFINE(f32, float, float, float)
 REF_DEFINE(f64, double, double, double)
+REF_DEFINE_EXT(f32, float)
+REF_DEFINE_EXT(f64, double)
 #ifdef BLAS_ENABLE_HALF
 REF_DEFINE(f16, sycl::half, sycl::half, float)
 REF_DEFINE(f16f32, sycl::half, float, float)

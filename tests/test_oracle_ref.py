@@ -260,3 +260,71 @@ def test_ref_host_golden():
             else:
                 ref_host.gemm(ta, tb, m, nn, k, al, A, lda, B, ldb, be, again, ldc, backend=backend)
             assert np.array_equal(again, want)
+
+
+# ---- the two callers of the path that the reference implements on top of _gemm: _symm and _trsm -------
+def test_symm_of_the_reference_is_the_restated_gemm_on_the_mirrored_matrix(ref_libs):
+    """blas::_symm = _gemm_backend with a mirroring operand loader (symm_interface.hpp:35-71, gemm_local.hpp:813-873).
+    Grid of blas3_symm_test.cpp:155-209 (reduced): the reference's result must equal, bit for bit, the restated GEMM
+    (production ordering) applied to the explicitly mirrored matrix -- which is how pbx_symm is built -- and agree with
+    the ext oracle (long-double) and CBLAS under the reference's predicate."""
+    from oracle import blas3_ext as ox
+    rng = np.random.default_rng(41)
+    for npdt, kind in ((np.float32, "float"), (np.float64, "double")):
+        for side, uplo, (m, n), (al, be), (la, lb, lc) in itertools.product("lr", "ul", [(14, 9), (63, 40), (127, 130)],
+                                                                            [(1.5, 0.5), (3.0, 0.0)], [(1, 1, 1), (2, 3, 4)]):
+            k = m if side == "l" else n
+            lda, ldb, ldc = k * la, m * lb, m * lc
+            A = oracle.random_uniform(rng, k * lda, npdt)
+            B = oracle.random_uniform(rng, n * ldb, npdt)
+            C = oracle.random_uniform(rng, n * ldc, npdt)
+            want = C.copy()
+            ref_host.symm(side, uplo, m, n, al, A, lda, B, ldb, be, want, ldc)
+            full = np.asfortranarray(ox.symm_full(uplo, k, A, lda)).ravel(order="F").copy()
+            got = C.copy()
+            if side == "l":
+                oracle.gemm("n", "n", m, n, k, al, full, k, B, ldb, be, got, ldc, mode=oracle.MODE_LOCAL)
+            else:
+                oracle.gemm("n", "n", m, n, k, al, B, ldb, full, k, be, got, ldc, mode=oracle.MODE_LOCAL)
+            assert np.array_equal(got, want), (npdt.__name__, side, uplo, m, n, al, be, la)
+            truth = C.copy()
+            assert ox.symm(side, uplo, m, n, al, A, lda, B, ldb, be, truth, ldc) == 0
+            assert oracle.compare(want, truth, kind) == 0
+    A = oracle.random_uniform(rng, 64, np.float32)
+    for side, uplo, msg in (("l", "x", "invalid _uplo"), ("q", "u", "invalid _side")):
+        with pytest.raises(ref_host.ReferenceError_, match=msg):
+            ref_host.symm(side, uplo, 8, 8, 1.0, A, 8, A, 8, 0.0, A.copy(), 8)
+        assert ox.STATUS_TEXT[ox.symm_status(side, uplo)] == msg
+
+
+def test_trsm_of_the_reference_against_the_restated_scheme(ref_libs):
+    """blas::_trsm (trsm_interface.hpp:150-387: 16-wide DiagonalBlocksInverter blocks, then the GEMM loop) on the grid of
+    blas3_trsm_test.cpp:130-163 (reduced; NaN in the unused triangle included): the ext oracle's restatement of that
+    scheme agrees with the reference's output far inside the reference's own margins, both agree with CBLAS under
+    almost_equal, and the validation messages are the reference's."""
+    from oracle import blas3_ext as ox
+    rng = np.random.default_rng(43)
+    for npdt, kind, tight in ((np.float32, "float", 2e-5), (np.float64, "double", 1e-13)):
+        for side, uplo, trans, diag, (m, n), unused in itertools.product("lr", "ul", "nt", "un", [(7, 9), (33, 17), (70, 45)],
+                                                                         [0.0, np.nan]):
+            k = m if side == "l" else n
+            lda, ldb = k * 2, m * 3
+            A = ox.fill_trsm_matrix(rng, k, lda, uplo, diag, 5.0, unused, npdt)
+            B = oracle.random_uniform(rng, n * ldb, npdt)
+            want, model, cb = B.copy(), B.copy(), B.copy()
+            ref_host.trsm(side, uplo, trans, diag, m, n, 2.0, A, lda, want, ldb)
+            assert ox.trsm_ref_algorithm(side, uplo, trans, diag, m, n, 2.0, A, lda, model, ldb) == 0
+            ox.cblas_trsm(side, uplo, trans, diag, m, n, 2.0, np.nan_to_num(A), lda, cb, ldb)
+            what = (npdt.__name__, side, uplo, trans, diag, m, n, unused)
+            assert not np.isnan(want).any(), what
+            assert oracle.compare(want, cb, kind) == 0, what
+            scale = np.abs(cb).max()
+            assert np.abs(want.astype(np.float64) - model.astype(np.float64)).max() <= tight * scale, what
+    A = oracle.random_uniform(rng, 64, np.float32)
+    for args, msg in ((("x", "u", "n", "n"), "invalid Side argument"), (("l", "x", "n", "n"), "invalid Triangle argument"),
+                      (("l", "u", "x", "n"), "invalid Transpose argument"), (("l", "u", "n", "x"), "invalid Diagonal argument")):
+        with pytest.raises(ref_host.ReferenceError_, match=msg):
+            ref_host.trsm(*args, 8, 8, 1.0, A, 8, A.copy(), 8)
+        assert ox.STATUS_TEXT[ox.trsm_status(*args, 8, 8, 8, 8)] == msg
+    with pytest.raises(ref_host.ReferenceError_, match="invalid matrix size argument"):
+        ref_host.trsm("l", "u", "n", "n", 0, 8, 1.0, A, 8, A.copy(), 8)

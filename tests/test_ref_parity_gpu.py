@@ -170,3 +170,53 @@ def test_half_matches_the_reference_live(handle, ref_libs):
         ref_host.gemm(ta, tb, m, n, k, 1.5, A, lda, B, ldb, 1.5, want16, ldc)
         got16 = _cuda(handle, torch.float16, ta, tb, m, n, k, 1.5, A, lda, B, ldb, 1.5, C, ldc)
         assert oracle.compare(got16.astype(np.float32), want16.astype(np.float32), "half") == 0, ("f16", ta, tb, m, n, k)
+
+
+def test_symm_and_trsm_match_the_reference_live(handle, ref_libs):
+    """pbx_symm / pbx_trsm beside the reference's own blas::_symm / blas::_trsm (symm_interface.hpp:35-71,
+    trsm_interface.hpp:150-387) on the reference's grids (blas3_symm_test.cpp:155-209, blas3_trsm_test.cpp:130-163 with NaN
+    in the unused triangle): _symm to the GEMM bound, _trsm (two different blockings of the same substitution, 16-wide
+    inverses there, 128 / 64-wide here) under the reference's predicate and 1e-4 / 1e-11 of the solution's scale."""
+    import torch
+    from oracle import blas3_ext as ox
+    from portblas_b200 import blas
+    rng = np.random.default_rng(81)
+    for (npdt, tdt, dt, kind, ttol) in ((np.float32, torch.float32, "f32", "float", 1e-4),
+                                        (np.float64, torch.float64, "f64", "double", 1e-11)):
+        for side, uplo, (m, n), (al, be) in itertools.product("lr", "ul", [(14, 9), (127, 130), (300, 264)],
+                                                              [(1.5, 0.5), (3.0, 0.0)]):
+            k = m if side == "l" else n
+            lda, ldb, ldc = k * 2, m * 3, m * 4
+            A = oracle.random_uniform(rng, k * lda, npdt)
+            B = oracle.random_uniform(rng, n * ldb, npdt)
+            C = oracle.random_uniform(rng, n * ldc, npdt)
+            want = C.copy()
+            ref_host.symm(side, uplo, m, n, al, A, lda, B, ldb, be, want, ldc)
+            a, b, c = (torch.from_numpy(x).cuda() for x in (A, B, C))
+            blas._symm(handle, side, uplo, m, n, al, a, lda, b, ldb, be, c, ldc)
+            handle.wait()
+            got = c.cpu().numpy()
+            full = np.abs(np.asfortranarray(ox.symm_full(uplo, k, A, lda)).ravel(order="F")).astype(np.float64)
+            bound = np.abs(C).astype(np.float64)
+            absB = np.abs(B).astype(np.float64)
+            if side == "l":
+                oracle.gemm("n", "n", m, n, k, abs(al), full, k, absB, ldb, abs(be), bound, ldc)
+            else:
+                oracle.gemm("n", "n", m, n, k, abs(al), absB, ldb, full, k, abs(be), bound, ldc)
+            _close(got, want, bound, REL[dt], ("symm", dt, side, uplo, m, n, al, be))
+            assert oracle.compare(got, want, kind) == 0
+        for side, uplo, trans, diag, (m, n), unused in itertools.product("lr", "ul", "nt", "un", [(33, 17), (200, 136)],
+                                                                         [0.0, np.nan]):
+            k = m if side == "l" else n
+            lda, ldb = k * 2, m * 3
+            A = ox.fill_trsm_matrix(rng, k, lda, uplo, diag, 5.0, unused, npdt)
+            B = oracle.random_uniform(rng, n * ldb, npdt)
+            want = B.copy()
+            ref_host.trsm(side, uplo, trans, diag, m, n, 2.0, A, lda, want, ldb)
+            a, b = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+            blas._trsm(handle, side, uplo, trans, diag, m, n, 2.0, a, lda, b, ldb)
+            handle.wait()
+            got = b.cpu().numpy()
+            what = ("trsm", dt, side, uplo, trans, diag, m, n, unused)
+            assert oracle.compare(got, want, kind) == 0, what
+            assert np.abs(got.astype(np.float64) - want.astype(np.float64)).max() <= ttol * np.abs(want).max(), what
