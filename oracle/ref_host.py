@@ -42,7 +42,7 @@ def lib_path(backend: str) -> Path:
 def build(force: bool = False) -> list:
     """Builds both libraries when the reference tree is present (idempotent); returns the libraries that exist."""
     if (REFERENCE / "src" / "interface" / "gemm_interface.hpp").exists():
-        srcs = [HERE / "ref_host_driver.cpp", HERE / "sycl_host" / "sycl" / "sycl.hpp", HERE / "Makefile"]
+        srcs = [HERE / "ref_host_driver.cpp", HERE / "Makefile", *(HERE / "sycl_host").rglob("*.hpp")]
         newest = max(p.stat().st_mtime for p in srcs)
         stale = force or any(not lib_path(b).exists() or lib_path(b).stat().st_mtime < newest for b in BACKENDS)
         if stale:
@@ -73,6 +73,10 @@ def lib(backend: str = "default") -> ctypes.CDLL:
         for sfx, ct in (("f32", ctypes.c_float), ("f64", ctypes.c_double)):
             getattr(L, f"ref_symm_{sfx}").argtypes = [c, c, i, i, ct, vp, i, vp, i, ct, vp, i]
             getattr(L, f"ref_trsm_{sfx}").argtypes = [c, c, c, c, i, i, ct, vp, i, vp, i]
+        for sfx, ct in (("c64", ctypes.c_float), ("c128", ctypes.c_double)):
+            getattr(L, f"ref_gemm_{sfx}").argtypes = [c, c, i, i, i, ct, ct, vp, i, vp, i, ct, ct, vp, i]
+            getattr(L, f"ref_gemm_strided_batched_{sfx}").argtypes = [c, c, i, i, i, ct, ct, vp, i, i, vp, i, i, ct, ct, vp,
+                                                                      i, i, i]
         assert L.ref_backend().decode() == backend
         _libs[backend] = L
     return _libs[backend]
@@ -87,6 +91,9 @@ def _check(L, rc):
         raise ReferenceError_(L.ref_last_error().decode())
 
 
+_CPLX = {np.dtype(np.complex64): "c64", np.dtype(np.complex128): "c128"}
+
+
 def _suffix(A: np.ndarray, C: np.ndarray) -> str:
     for sfx, (ti, to, _) in TYPES.items():
         if A.dtype == ti and C.dtype == to:
@@ -99,8 +106,14 @@ def _b(ch: str) -> bytes:
 
 
 def gemm(ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, *, backend="default") -> None:
-    """blas::_gemm on flat column-major numpy buffers, C in place."""
+    """blas::_gemm on flat column-major numpy buffers, C in place (complex64 / complex128 buffers take the reference's
+    complex instantiations, BLAS_ENABLE_COMPLEX)."""
     L = lib(backend)
+    if C.dtype in _CPLX:
+        al, be = complex(alpha), complex(beta)
+        return _check(L, getattr(L, f"ref_gemm_{_CPLX[C.dtype]}")(_b(ta), _b(tb), m, n, k, al.real, al.imag, A.ctypes.data,
+                                                                 lda, B.ctypes.data, ldb, be.real, be.imag,
+                                                                 C.ctypes.data, ldc))
     sfx = _suffix(A, C)
     _check(L, getattr(L, f"ref_gemm_{sfx}")(_b(ta), _b(tb), m, n, k, alpha, A.ctypes.data, lda, B.ctypes.data, ldb,
                                             beta, C.ctypes.data, ldc))
@@ -119,6 +132,11 @@ def gemm_strided_batched(ta, tb, m, n, k, alpha, A, lda, stride_a, B, ldb, strid
                          backend="default") -> None:
     """blas::_gemm_strided_batched."""
     L = lib(backend)
+    if C.dtype in _CPLX:
+        al, be = complex(alpha), complex(beta)
+        return _check(L, getattr(L, f"ref_gemm_strided_batched_{_CPLX[C.dtype]}")(
+            _b(ta), _b(tb), m, n, k, al.real, al.imag, A.ctypes.data, lda, stride_a, B.ctypes.data, ldb, stride_b, be.real,
+            be.imag, C.ctypes.data, ldc, stride_c, batch))
     sfx = _suffix(A, C)
     _check(L, getattr(L, f"ref_gemm_strided_batched_{sfx}")(_b(ta), _b(tb), m, n, k, alpha, A.ctypes.data, lda, stride_a,
                                                             B.ctypes.data, ldb, stride_b, beta, C.ctypes.data, ldc,

@@ -134,4 +134,31 @@ REF_DEFINE(f16, sycl::half, sycl::half, float)
 REF_DEFINE(f16f32, sycl::half, float, float)
 #endif
 
+#ifdef BLAS_ENABLE_COMPLEX
+// complex<float> / complex<double> GEMM (gemm.cpp.in complex instantiations; blas3_gemm_test.cpp:143-259).  Buffers are
+// interleaved (re, im) pairs, the layout of std::complex and of the reference's device type alike; alpha and beta arrive
+// as two reals each.
+#define REF_DEFINE_CPLX(SUFFIX, T)                                                                                  \
+  int ref_gemm_##SUFFIX(char ta, char tb, int m, int n, int k, T alpha_re, T alpha_im, const void* A, int lda,     \
+                        const void* B, int ldb, T beta_re, T beta_im, void* C, int ldc) {                           \
+    using cplx = blas::complex_sycl<T>;                                                                            \
+    return guarded([&] {                                                                                            \
+      blas::_gemm(handle(), ta, tb, m, n, k, cplx(alpha_re, alpha_im), static_cast<const cplx*>(A), lda,            \
+                  static_cast<const cplx*>(B), ldb, cplx(beta_re, beta_im), static_cast<cplx*>(C), ldc, {});        \
+    });                                                                                                             \
+  }                                                                                                                 \
+  int ref_gemm_strided_batched_##SUFFIX(char ta, char tb, int m, int n, int k, T alpha_re, T alpha_im,             \
+                                        const void* A, int lda, int stride_a, const void* B, int ldb, int stride_b, \
+                                        T beta_re, T beta_im, void* C, int ldc, int stride_c, int batch) {          \
+    using cplx = blas::complex_sycl<T>;                                                                            \
+    return guarded([&] {                                                                                            \
+      blas::_gemm_strided_batched(handle(), ta, tb, m, n, k, cplx(alpha_re, alpha_im), static_cast<const cplx*>(A), \
+                                  lda, stride_a, static_cast<const cplx*>(B), ldb, stride_b, cplx(beta_re, beta_im), \
+                                  static_cast<cplx*>(C), ldc, stride_c, batch, {});                                 \
+    });                                                                                                             \
+  }
+REF_DEFINE_CPLX(c64, float)
+REF_DEFINE_CPLX(c128, double)
+#endif
+
 }  // extern "C"

@@ -328,3 +328,40 @@ def test_trsm_of_the_reference_against_the_restated_scheme(ref_libs):
         assert ox.STATUS_TEXT[ox.trsm_status(*args, 8, 8, 8, 8)] == msg
     with pytest.raises(ref_host.ReferenceError_, match="invalid matrix size argument"):
         ref_host.trsm("l", "u", "n", "n", 0, 8, 1.0, A, 8, A.copy(), 8)
+
+
+def test_complex_gemm_of_the_reference(ref_libs):
+    """complex<float> / complex<double> (BLAS_ENABLE_COMPLEX; grids of blas3_gemm_test.cpp:143-259, reduced) through the
+    reference's own complex kernels (default.hpp:202-246: no-local Tile<2,2,4,4> / Tile<8,8,4,4>; nvidia_gpu.hpp:237-260):
+    the ext oracle's cgemm -- INCLUDING its restatement of the reference's quirk that 'c' is handled as 't', without
+    conjugation -- agrees under the reference's predicate and to 1e-5 / 1e-12 of |alpha||A||B| + |beta||C|; the BLAS
+    meaning of 'c' (conjugate) demonstrably does not."""
+    from oracle import blas3_ext as ox
+    rng = np.random.default_rng(47)
+
+    def rnd(count, cdt):
+        return (rng.uniform(-2, 5, count) + 1j * rng.uniform(-2, 5, count)).astype(cdt)
+
+    for backend, (cdt, kind, rel) in itertools.product(["default", "nvidia_gpu"],
+                                                       [(np.complex64, "float", 1e-5), (np.complex128, "double", 1e-12)]):
+        for ta, tb, (m, n, k), (al, be), lm in itertools.product("ntc", "ntc", [(11, 16, 17), (63, 33, 40), (260, 40, 300)],
+                                                                 [(1.5 + 0.5j, 0.5 - 1j), (1 + 0j, 0j)], [1, 2]):
+            lda, ldb, ldc = (k if ta != "n" else m) * lm, (n if tb != "n" else k) * lm, m * lm
+            A, B, C = rnd(m * k * lm, cdt), rnd(k * n * lm, cdt), rnd(m * n * lm, cdt)
+            want, got = C.copy(), C.copy()
+            ref_host.gemm(ta, tb, m, n, k, al, A, lda, B, ldb, be, want, ldc, backend=backend)
+            assert ox.cgemm(ta, tb, m, n, k, al, A, lda, B, ldb, be, got, ldc) == 0
+            what = (backend, cdt.__name__, ta, tb, m, n, k, al, be, lm)
+            assert oracle.compare(got.view(got.real.dtype), want.view(want.real.dtype), kind) == 0, what
+            bound = np.abs(C).astype(np.float64)
+            oracle.gemm("t" if ta != "n" else "n", "t" if tb != "n" else "n", m, n, k, abs(al), np.abs(A).astype(np.float64),
+                        lda, np.abs(B).astype(np.float64), ldb, abs(be), bound, ldc)
+            assert (np.abs(got.astype(np.complex128) - want) <= rel * 2 * bound + 1e-300).all(), what
+    # 'c' really is 't' in the reference
+    m, n, k = 9, 7, 8
+    A, B, C = rnd(m * k, np.complex128), rnd(k * n, np.complex128), rnd(m * n, np.complex128)
+    as_c, as_t, blas_c = C.copy(), C.copy(), C.copy()
+    ref_host.gemm("c", "n", m, n, k, 1.0, A, k, B, k, 0.0, as_c, m)
+    ref_host.gemm("t", "n", m, n, k, 1.0, A, k, B, k, 0.0, as_t, m)
+    ox.cgemm("c", "n", m, n, k, 1.0, A, k, B, k, 0.0, blas_c, m, conj=True)
+    assert np.array_equal(as_c, as_t) and np.abs(as_c - blas_c).max() > 1.0

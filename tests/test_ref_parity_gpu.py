@@ -220,3 +220,34 @@ def test_symm_and_trsm_match_the_reference_live(handle, ref_libs):
             what = ("trsm", dt, side, uplo, trans, diag, m, n, unused)
             assert oracle.compare(got, want, kind) == 0, what
             assert np.abs(got.astype(np.float64) - want.astype(np.float64)).max() <= ttol * np.abs(want).max(), what
+
+
+def test_complex_gemm_matches_the_reference_live(handle, ref_libs):
+    """pbx_cgemm / pbx_zgemm beside the reference's own complex GEMM (BLAS_ENABLE_COMPLEX; 'c' handled as 't', as the
+    reference does) on the grid of blas3_gemm_test.cpp:143-259 (reduced): 1e-5 / 1e-12 of |alpha||A||B| + |beta||C|."""
+    import torch
+    from portblas_b200 import blas
+    rng = np.random.default_rng(82)
+
+    def rnd(count, cdt):
+        return (rng.uniform(-2, 5, count) + 1j * rng.uniform(-2, 5, count)).astype(cdt)
+
+    for cdt, rel in ((np.complex64, 1e-5), (np.complex128, 1e-12)):
+        for ta, tb, (m, n, k), (al, be) in itertools.product("ntc", "ntc", [(11, 16, 17), (63, 33, 40), (260, 136, 300)],
+                                                             [(1.5 + 0.5j, 0.5 - 1j), (1 + 0j, 0j)]):
+            lda, ldb, ldc = (k if ta != "n" else m) * 2, (n if tb != "n" else k) * 2, m * 2
+            A, B, C = rnd(m * k * 2, cdt), rnd(k * n * 2, cdt), rnd(m * n * 2, cdt)
+            want = C.copy()
+            ref_host.gemm(ta, tb, m, n, k, al, A, lda, B, ldb, be, want, ldc, backend="nvidia_gpu")
+            a, b, c = (torch.from_numpy(x).cuda() for x in (A, B, C))
+            blas._gemm(handle, ta, tb, m, n, k, al, a, lda, b, ldb, be, c, ldc)
+            handle.wait()
+            got = c.cpu().numpy()
+            bound = np.abs(C).astype(np.float64)
+            oracle.gemm("t" if ta != "n" else "n", "t" if tb != "n" else "n", m, n, k, abs(al), np.abs(A).astype(np.float64),
+                        lda, np.abs(B).astype(np.float64), ldb, abs(be), bound, ldc)
+            what = ("cgemm", cdt.__name__, ta, tb, m, n, k, al, be)
+            assert (np.abs(got.astype(np.complex128) - want) <= rel * 2 * bound + 1e-300).all(), what
+            pad = np.ones(C.shape, bool)
+            pad.reshape(n, ldc)[:, :m] = False
+            assert np.array_equal(got[pad], C[pad]), what
