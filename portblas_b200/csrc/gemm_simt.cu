@@ -414,6 +414,31 @@ __global__ void __launch_bounds__(256) tf32_lo_kernel(const float* __restrict__ 
   }
 }
 
+// ---- fp32 operand -> two bf16 copies for the tf32 + 2 x bf16 product (EXPERIMENTAL, PBX_F32_SPLIT16=1) ----------
+// hi16 = bf16(a), lo16 = bf16(a - trunc_tf32(a)); the copies have their own leading dimension / batch stride (multiples
+// of 8 elements, so that they are TMA-legal whatever the source's were).  One warp per 2048-row chunk of a column.
+__global__ void __launch_bounds__(256) split16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
+                                                      __nv_bfloat16* __restrict__ lo, int64_t rows, int64_t cols,
+                                                      int64_t ld, int64_t stride, int64_t ld16, int64_t st16,
+                                                      int64_t batch, int64_t chunks) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t units = batch * cols * chunks;
+  for (int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < units; u += nwarps) {
+    const int64_t chunk = u % chunks, col = (u / chunks) % cols, b = u / (chunks * cols);
+    const int64_t r0 = chunk * 2048, r1 = min(rows, r0 + 2048);
+    const float* s = src + b * stride + col * ld;
+    __nv_bfloat16* dh = hi + b * st16 + col * ld16;
+    __nv_bfloat16* dl = lo + b * st16 + col * ld16;
+    for (int64_t r = r0 + lane; r < r1; r += 32) {
+      const float x = s[r];
+      const float d = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+      dh[r] = __float2bfloat16_rn(x);
+      dl[r] = __float2bfloat16_rn(d == d ? d : 0.0f);   // inf - inf -> 0
+    }
+  }
+}
+
 // ---- C <- beta*C ---------------------------------------------------------------
 template <typename TOut, typename TAcc>
 __global__ void __launch_bounds__(256) scal_matrix_kernel(TOut* C, int64_t m, int64_t n, int64_t ldc,
@@ -526,6 +551,21 @@ int pbx_launch_tf32_lo(pbx_handle_t h, const float* src, float* dst, int64_t row
   const int64_t cap = (int64_t)h->sm_count * 16;
   if (blocks > cap) blocks = cap;
   tf32_lo_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(src, dst, rows, cols, ld, stride, batch, chunks);
+  h->launches++;
+  PBX_CUDA_CHECK(h, cudaGetLastError());
+  return PBX_OK;
+}
+
+int pbx_launch_split16(pbx_handle_t h, const float* src, void* hi, void* lo, int64_t rows, int64_t cols, int64_t ld,
+                       int64_t stride, int64_t ld16, int64_t st16, int64_t batch) {
+  if (rows <= 0 || cols <= 0 || batch <= 0) return PBX_OK;
+  const int64_t chunks = (rows + 2047) / 2048;
+  const int64_t units = batch * cols * chunks;
+  int64_t blocks = (units + 7) / 8;   // 8 warps per block
+  const int64_t cap = (int64_t)h->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  split16_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(src, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, rows, cols, ld,
+                                                          stride, ld16, st16, batch, chunks);
   h->launches++;
   PBX_CUDA_CHECK(h, cudaGetLastError());
   return PBX_OK;

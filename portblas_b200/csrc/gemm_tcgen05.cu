@@ -99,6 +99,12 @@ constexpr int ROW_BYTES = 128;  // one swizzle row
 //   2  single tf32 product (no lo halves at all): the reduced-precision mode the reference reaches with
 //      SB_ENABLE_JOINT_MATRIX=1 (float storage, 10-bit-mantissa fragments, fp32 accumulate,
 //      src/interface/blas3/backend/nvidia_gpu.hpp:67-110); stages hold raw tiles only, so the ring is twice as deep
+//   3  tf32 + 2 x bf16 (EXPERIMENTAL, PBX_F32_SPLIT16=1, not yet run on a GPU): A_hi*B_hi as one tf32 MMA on the raw
+//      tiles, the two cross terms as kind::f16 MMAs on bf16 copies made by a pre-pass (bf16(a) and bf16(a - trunc_tf32(a))):
+//      the lo halves are 2^-11 of the operand, so 8 bits of them keep the product inside the 1e-5 budget
+//      (tools/split_emulation.py: <= 2e-7 of sum|a||b|), and bf16 MMAs run at twice the tf32 rate -- two tf32-MMA
+//      times per k-step instead of three.  The bf16 tiles are 32 k wide like the fp32 ones (64-byte rows, 64B swizzle)
+//      and take the place of the lo tiles in the stage: [A raw | B raw | A16 hi | A16 lo | B16 hi | B16 lo]
 template <int ES, int BN, int STAGES, int CG, int OS = 4, int PRE = 0>
 struct TcCfg {
   static constexpr bool TF32X3 = (ES == 4);
@@ -122,7 +128,7 @@ struct TcCfg {
   static constexpr int RSUM_COL = ACC_STAGES * BN;
   static constexpr int TMEM_COLS = TF32X3 ? 512 : 2 * BN;
   static constexpr int SPLIT_WARPS = (TF32X3 && PRE == 0) ? 4 : 0;
-  static constexpr int TMA_BYTES = RAW_BYTES * ((TF32X3 && PRE == 1) ? 2 : 1);   // bytes one CTA's producer lands per stage
+  static constexpr int TMA_BYTES = RAW_BYTES * ((TF32X3 && (PRE == 1 || PRE == 3)) ? 2 : 1);   // bytes one CTA's producer lands per stage
   static constexpr int NUM_THREADS = 32 * (4 + EPI_WARPS + SPLIT_WARPS);
   static constexpr int NUM_SPLIT_THREADS = 32 * SPLIT_WARPS;
   static_assert(BN % (32 * 2) == 0 && BN <= 256 && (BN_CTA % 8) == 0, "tile width");
@@ -185,7 +191,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (Cfg::EPI_BYTES > 0 && p.tma_store) tma_prefetch_desc(&tmC);
-    if (PRE == 1) { tma_prefetch_desc(&tmAlo); tma_prefetch_desc(&tmBlo); }
+    if (PRE == 1 || PRE == 3) { tma_prefetch_desc(&tmAlo); tma_prefetch_desc(&tmBlo); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -262,6 +268,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               load(sBl, &tmBlo, kb * BK, n0, zb);
             }
           }
+          if (PRE == 3) {
+            // bf16 copies (tmAlo = A's, tmBlo = B's): z = which * copies + batch entry, which = 0 (hi) / 1 (lo);
+            // K-major: one box of 32 k x rows; MN-major: boxes of 32 mn x 32 k (2 KiB each, 64-byte rows)
+            const uint32_t s16 = sA + Cfg::RAW_BYTES;
+            const int ca = p.a_batched ? p.batch : 1, cb = p.b_batched ? p.batch : 1;
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+              const uint32_t dA = s16 + w * (Cfg::A_BYTES / 2);
+              const uint32_t dB = s16 + Cfg::A_BYTES + w * (Cfg::B_BYTES / 2);
+              if (A_MN) {
+#pragma unroll
+                for (int c = 0; c < BM / 32; ++c) load(dA + c * 2048, &tmAlo, m0 + c * 32, kb * BK, w * ca + za);
+              } else {
+                load(dA, &tmAlo, kb * BK, m0, w * ca + za);
+              }
+              if (B_MN) {
+#pragma unroll
+                for (int c = 0; c < Cfg::BN_CTA / 32; ++c) load(dB + c * 2048, &tmBlo, n0 + c * 32, kb * BK, w * cb + zb);
+              } else {
+                load(dB, &tmBlo, kb * BK, n0, w * cb + zb);
+              }
+            }
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -310,7 +339,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint64_t adesc = make_smem_desc(sA + k * A_KSTEP, A_LBO, A_SBO, A_LT);
               const uint64_t bdesc = make_smem_desc(sB + k * B_KSTEP, B_LBO, B_SBO, B_LT);
               const uint32_t acc = (kb > kc0 || k > 0) ? 1u : 0u;
-              if (TF32X3 && PRE != 2) {
+              if (PRE == 3) {
+                mma(d_tmem, adesc, bdesc, acc);   // hi * hi (tf32 on the raw tiles); the cross terms follow per k-block
+              } else if (TF32X3 && PRE != 2) {
                 const uint64_t adesc_lo = make_smem_desc(sA + Cfg::RAW_BYTES + k * A_KSTEP, A_LBO, A_SBO, A_LT);
                 const uint64_t bdesc_lo = make_smem_desc(sB + Cfg::RAW_BYTES + k * B_KSTEP, B_LBO, B_SBO, B_LT);
                 mma(d_tmem, adesc_lo, bdesc, acc);
@@ -318,6 +349,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mma(d_tmem, adesc, bdesc, 1u);
               } else {
                 mma(d_tmem, adesc, bdesc, acc);
+              }
+            }
+            if (PRE == 3) {
+              // cross terms on the bf16 tiles: 64-byte rows (K-major) / 64-byte mn chunks (MN-major), 64B swizzle
+              // (layout type 4): SBO = 8 rows x 64 B; MN-major LBO = one 32 x 32 box; UMMA_K = 16
+              constexpr uint32_t idesc16 = make_idesc(1u, A_MN, B_MN, BN, Cfg::TILE_M);
+              constexpr uint32_t A16_KSTEP = A_MN ? 16 * 64 : 32, B16_KSTEP = B_MN ? 16 * 64 : 32;
+              constexpr uint32_t A16_LBO = A_MN ? 2048 : 16, B16_LBO = B_MN ? 2048 : 16;
+              const uint32_t sA16 = sA + Cfg::RAW_BYTES, sB16 = sA16 + Cfg::A_BYTES;
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint64_t a_hi = make_smem_desc(sA16 + k * A16_KSTEP, A16_LBO, 512u, 4u);
+                const uint64_t a_lo = make_smem_desc(sA16 + Cfg::A_BYTES / 2 + k * A16_KSTEP, A16_LBO, 512u, 4u);
+                const uint64_t b_hi = make_smem_desc(sB16 + k * B16_KSTEP, B16_LBO, 512u, 4u);
+                const uint64_t b_lo = make_smem_desc(sB16 + Cfg::B_BYTES / 2 + k * B16_KSTEP, B16_LBO, 512u, 4u);
+                if (CG == 2) {
+                  tc_mma_2sm<false>(d_tmem, a_lo, b_hi, idesc16, 1u);
+                  tc_mma_2sm<false>(d_tmem, a_hi, b_lo, idesc16, 1u);
+                } else {
+                  tc_mma<false>(d_tmem, a_lo, b_hi, idesc16, 1u);
+                  tc_mma<false>(d_tmem, a_hi, b_lo, idesc16, 1u);
+                }
               }
             }
             commit(empty_bar(stage));  // smem slot (both CTAs) reusable once these MMAs retire
@@ -626,6 +679,22 @@ bool make_operand_map(CUtensorMap* out, int es, CUtensorMapDataType dt, const vo
   return r == CUDA_SUCCESS;
 }
 
+// Tensor map of the bf16 copies of one fp32 operand (PRE == 3): the hi copies of all batch entries, then the lo copies,
+// along z (z = which * copies + b; zstride elements apart); 32-element (64-byte) rows, 64B swizzle.
+bool make_split16_map(CUtensorMap* out, const void* ptr, int64_t mn, int64_t k, int64_t ld16, int64_t copies,
+                      int64_t zstride, bool kcontig, int box_mn) {
+  auto fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)(kcontig ? k : mn), (cuuint64_t)(kcontig ? mn : k), (cuuint64_t)(2 * copies)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld16 * 2, (cuuint64_t)zstride * 2};
+  cuuint32_t box[3] = {32, (cuuint32_t)(kcontig ? box_mn : 32), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 // Tensor map of C for the TMA-store epilogue: 32 x 32 boxes of the column-major output, no swizzle.
 bool make_c_map(CUtensorMap* out, int es, CUtensorMapDataType dt, void* ptr, int64_t m, int64_t n, int64_t ld,
                 int64_t batch, int64_t stride) {
@@ -701,6 +770,7 @@ int launch_cfg(pbx_handle_t h, int cg, int bn, bool a_mn, bool b_mn, int pre, co
   if constexpr (sizeof(TIn) == 4) {
     if (pre == 1) return launch_cfg_pre<TIn, TOut, 1>(h, cg, bn, a_mn, b_mn, tm, p);
     if (pre == 2) return launch_cfg_pre<TIn, TOut, 2>(h, cg, bn, a_mn, b_mn, tm, p);
+    if (pre == 3) return launch_cfg_pre<TIn, TOut, 3>(h, cg, bn, a_mn, b_mn, tm, p);
   }
   return launch_cfg_pre<TIn, TOut, 0>(h, cg, bn, a_mn, b_mn, tm, p);
 }
@@ -842,7 +912,8 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
   // shared memory (measured: tensor pipe 68 % active at 16384^3); with the lo tiles arriving by TMA the
   // mainloop's shared-memory traffic drops by a quarter and the CTA needs no splitter warps.  Memory-bound
   // shapes (arithmetic intensity < 256 flop/B) keep the in-kernel split: the pre-pass would triple their traffic.
-  bool pre = false;
+  bool pre = false, split16 = false;
+  int64_t s16_ld[2] = {0, 0}, s16_z[2] = {0, 0}, s16_copies[2] = {1, 1};
   const void* lo_ptr[2] = {nullptr, nullptr};
   // SB_ENABLE_JOINT_MATRIX=1 is the reference's switch (read per call, nvidia_gpu.hpp:68-69) from the fp32 kernels to
   // its tensor-core kernels with reduced-precision fragments; here it selects the single-tf32 product.
@@ -853,7 +924,26 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
     const double flops = 2.0 * (double)c.m * (double)c.n * (double)c.k * (double)c.batch;
     const double byts = 4.0 * ((double)c.m * c.k + (double)c.k * c.n + (double)c.m * c.n) * (double)c.batch;
     pre = (pre_env >= 0) ? (pre_env != 0) : (flops >= 5e8 && flops / byts >= 256.0);
-    if (pre) {
+    // EXPERIMENTAL, off unless PBX_F32_SPLIT16=1 (written without a GPU at hand; see TcCfg's PRE == 3): tf32 + 2 x bf16.
+    // Takes the place of the fp32 lo pre-split on the shapes that would get it; same pooled buffers (2 x 2 bytes per
+    // element instead of 4), the copies laid out [hi of every batch entry | lo of every batch entry].
+    const char* s16_env = getenv("PBX_F32_SPLIT16");
+    if (pre && s16_env != nullptr && s16_env[0] == '1' && c.n_extra == 0) {
+      split16 = true;
+      const Opnd* ops[2] = {&X, &Y};
+      for (int i = 0; i < 2 && split16; ++i) {
+        const Opnd& o = *ops[i];
+        const int64_t rows = o.mn_major ? o.mn : c.k, cols = o.mn_major ? c.k : o.mn;
+        const int64_t copies = (c.batch > 1 && o.st > 0) ? c.batch : 1;
+        const int64_t ld16 = (rows + 7) / 8 * 8, st16 = ld16 * cols;   // multiples of 8 elements = 16 bytes
+        if (2 * copies >= ((int64_t)1 << 31) || pbx_ensure_lo(h, i, 2 * copies * st16 * 2) != PBX_OK ||
+            pbx_launch_split16(h, (const float*)o.p, h->lo[i], (char*)h->lo[i] + copies * st16 * 2, rows, cols, o.ld, o.st,
+                               ld16, st16, copies) != PBX_OK)
+          split16 = false;   // no room: the fp32 lo pre-split below takes over
+        s16_ld[i] = ld16; s16_z[i] = st16; s16_copies[i] = copies;
+      }
+    }
+    if (pre && !split16) {
       const Opnd* ops[2] = {&X, &Y};
       for (int i = 0; i < 2 && pre; ++i) {
         const Opnd& o = *ops[i];
@@ -876,12 +966,19 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
     return PBX_ERR_CUDA;
   }
   tm.alo = tm.a; tm.blo = tm.b;   // placeholders when unused (never dereferenced)
-  if (pre && (!make_operand_map(&tm.alo, es, dt, lo_ptr[0], X.mn, c.k, X.ld, c.batch, X.st, !a_mn, BM) ||
-              !make_operand_map(&tm.blo, es, dt, lo_ptr[1], Y.mn, c.k, Y.ld, c.batch, Y.st, !b_mn, bn / cg))) {
+  if (split16) {
+    if (!make_split16_map(&tm.alo, h->lo[0], X.mn, c.k, s16_ld[0], s16_copies[0], s16_z[0], !a_mn, BM) ||
+        !make_split16_map(&tm.blo, h->lo[1], Y.mn, c.k, s16_ld[1], s16_copies[1], s16_z[1], !b_mn, bn / cg)) {
+      h->last_error = "cuTensorMapEncodeTiled failed (bf16 split copies)";
+      return PBX_ERR_CUDA;
+    }
+  } else if (pre && (!make_operand_map(&tm.alo, es, dt, lo_ptr[0], X.mn, c.k, X.ld, c.batch, X.st, !a_mn, BM) ||
+                     !make_operand_map(&tm.blo, es, dt, lo_ptr[1], Y.mn, c.k, Y.ld, c.batch, Y.st, !b_mn, bn / cg))) {
     h->last_error = "cuTensorMapEncodeTiled failed";
     return PBX_ERR_CUDA;
   }
-  h->last_presplit = tf32x1 ? 2 : (pre ? 1 : 0);
+  const int pre_mode = tf32x1 ? 2 : (split16 ? 3 : (pre ? 1 : 0));
+  h->last_presplit = pre_mode;
   TcParams p;
   p.C = c.C; p.ws = (float*)h->ws;
   p.M = X.mn; p.N = Y.mn; p.K = c.k; p.ldc = c.ldc; p.sc = c.sc;
@@ -919,7 +1016,7 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
   }
 
   switch (c.dtype) {
-    case PBX_F32: return launch_cfg<float, float>(h, cg, bn, a_mn, b_mn, tf32x1 ? 2 : (pre ? 1 : 0), tm, p);
+    case PBX_F32: return launch_cfg<float, float>(h, cg, bn, a_mn, b_mn, pre_mode, tm, p);
     case PBX_F16: return launch_cfg<__half, __half>(h, cg, bn, a_mn, b_mn, tf32x1 ? 2 : (pre ? 1 : 0), tm, p);
     case PBX_F16_F32: return launch_cfg<__half, float>(h, cg, bn, a_mn, b_mn, tf32x1 ? 2 : (pre ? 1 : 0), tm, p);
     case PBX_BF16: return launch_cfg<__nv_bfloat16, __nv_bfloat16>(h, cg, bn, a_mn, b_mn, tf32x1 ? 2 : (pre ? 1 : 0), tm, p);

@@ -100,6 +100,9 @@ int pbx_ensure_lo(pbx_handle_t h, int i, int64_t bytes);
 // lo = rn_tf32(x - trunc_tf32(x)) over a rows x cols column-major window (x batch), same ld / stride as the source
 int pbx_launch_tf32_lo(pbx_handle_t h, const float* src, float* dst, int64_t rows, int64_t cols, int64_t ld,
                        int64_t stride, int64_t batch);
+// EXPERIMENTAL (PBX_F32_SPLIT16=1): bf16(a) and bf16(a - trunc_tf32(a)) copies of an fp32 operand with their own ld / stride
+int pbx_launch_split16(pbx_handle_t h, const float* src, void* hi, void* lo, int64_t rows, int64_t cols, int64_t ld,
+                       int64_t stride, int64_t ld16, int64_t st16, int64_t batch);
 
 // ---- kernel families (each returns a pbx_status_t) -----------------------
 // slices > 1: the kernel writes raw fp32/fp64 partial sums to h->ws laid out
