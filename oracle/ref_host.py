@@ -52,6 +52,26 @@ def build(force: bool = False) -> list:
     return [lib_path(b) for b in BACKENDS if lib_path(b).exists()]
 
 
+REF_TESTS = ("blas3_gemm_test", "blas3_gemm_batched_test", "blas3_gemm_tall_skinny_test", "blas3_symm_test",
+             "blas3_trsm_test")
+
+
+def unittest_path(name: str) -> Path:
+    return REF_DIR / f"ref_unittest_host_{name}"
+
+
+def build_unittests() -> list:
+    """The reference's own unit tests linked with the reference's own (header-only) library on the host stand-in
+    (`make -C oracle ref_tests`); built when the reference tree is present, returns the binaries that exist."""
+    if (REFERENCE / "test" / "unittest" / "main.cpp").exists():
+        newest = max(p.stat().st_mtime for p in [HERE / "Makefile", *(HERE / "sycl_host").rglob("*.hpp")])
+        if any(not unittest_path(t).exists() or unittest_path(t).stat().st_mtime < newest for t in REF_TESTS):
+            r = subprocess.run(["make", "-C", str(HERE), "-j5", "-B", "ref_tests"], capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("reference unit tests (host) build failed:\n" + r.stdout[-3000:] + r.stderr[-3000:])
+    return [unittest_path(t) for t in REF_TESTS if unittest_path(t).exists()]
+
+
 def available(backend: str = "default") -> bool:
     return lib_path(backend).exists()
 

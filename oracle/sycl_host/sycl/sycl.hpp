@@ -55,6 +55,9 @@ class exception : public std::runtime_error {
  public:
   explicit exception(const std::string& m) : std::runtime_error(m) {}
 };
+using exception_list = std::vector<std::exception_ptr>;
+using async_handler = std::function<void(exception_list)>;
+enum class aspect { fp16, fp64, gpu, cpu };
 
 // ---------------------------------------------------------------- index space
 template <int D = 1>
@@ -294,9 +297,17 @@ struct max_work_group_size { using return_type = size_t; };
 struct local_mem_size { using return_type = size_t; };
 struct local_mem_type { using return_type = int; };
 struct sub_group_sizes { using return_type = std::vector<size_t>; };
-struct device_type { using return_type = int; };
+struct device_type;
+struct version { using return_type = std::string; };
+struct driver_version { using return_type = std::string; };
 }  // namespace device
-enum class device_type { cpu, gpu, accelerator, host, all };
+enum class device_type { cpu, gpu, accelerator, custom, automatic, host, all };
+namespace device {
+struct device_type { using return_type = info::device_type; };
+}  // namespace device
+namespace platform {
+struct name { using return_type = std::string; };
+}  // namespace platform
 namespace local_mem_type_ns {
 enum type : int { none = 0, local = 1, global = 2 };
 }
@@ -304,6 +315,7 @@ struct local_mem_type {  // usable both as sycl::info::local_mem_type::local and
   static constexpr int none = 0, local = 1, global = 2;
 };
 namespace event_profiling {
+struct command_submit { using return_type = uint64_t; };
 struct command_start { using return_type = uint64_t; };
 struct command_end { using return_type = uint64_t; };
 }  // namespace event_profiling
@@ -311,12 +323,23 @@ struct command_end { using return_type = uint64_t; };
 
 int host_compute_units();  // OpenMP threads available to the executor
 
+class platform {
+ public:
+  template <typename P>
+  typename P::return_type get_info() const { return "host stand-in (oracle/sycl_host)"; }
+};
+
 class device {
  public:
+  platform get_platform() const { return platform(); }
+  bool has(aspect a) const { return a != aspect::gpu; }
   template <typename P>
   typename P::return_type get_info() const {
     if constexpr (std::is_same_v<P, info::device::name>) return "host stand-in (oracle/sycl_host)";
     else if constexpr (std::is_same_v<P, info::device::vendor>) return "none";
+    else if constexpr (std::is_same_v<P, info::device::device_type>) return info::device_type::cpu;
+    else if constexpr (std::is_same_v<P, info::device::version> || std::is_same_v<P, info::device::driver_version>)
+      return "g++ host executor";
     else if constexpr (std::is_same_v<P, info::device::max_compute_units>) return (unsigned)host_compute_units();
     else if constexpr (std::is_same_v<P, info::device::max_work_group_size>) return (size_t)1024;
     else if constexpr (std::is_same_v<P, info::device::local_mem_size>) return (size_t)(64 * 1024);
@@ -366,6 +389,8 @@ class buffer {
 
 class handler;
 
+// Ranged accessors follow SYCL 2020: get_pointer() and operator[] are relative to the START OF THE BUFFER (portBLAS's views
+// add the offset themselves: ptr_ = data_.get_pointer() + disp_); only handler::copy / fill act on [offset, offset + range).
 template <typename T, int D = 1, access_mode M = access_mode::read_write, target Tg = target::device,
           access::placeholder P = access::placeholder::false_t>
 class accessor {
@@ -373,9 +398,9 @@ class accessor {
   using value_type = T;
   accessor() = default;
   template <typename U>
-  accessor(buffer<U, D> b, handler&, range<D> r, id<D> off = id<D>(0)) : p_(b.host_data() + off.v), n_(r.size()) {}
+  accessor(buffer<U, D> b, handler&, range<D> r, id<D> off = id<D>(0)) : p_(b.host_data()), n_(r.size()), off_(off.v) {}
   template <typename U>
-  accessor(buffer<U, D> b, range<D> r, id<D> off = id<D>(0)) : p_(b.host_data() + off.v), n_(r.size()) {}
+  accessor(buffer<U, D> b, range<D> r, id<D> off = id<D>(0)) : p_(b.host_data()), n_(r.size()), off_(off.v) {}
   template <typename U>
   accessor(buffer<U, D> b, handler&) : p_(b.host_data()), n_(b.size()) {}
   template <typename U>
@@ -387,11 +412,12 @@ class accessor {
   template <access::decorated Dec = access::decorated::legacy>
   global_ptr<T, Dec> get_multi_ptr() const { return global_ptr<T, Dec>(p_); }
   T& operator[](size_t i) const { return p_[i]; }
-  id<D> get_offset() const { return id<D>(0); }
+  id<D> get_offset() const { return id<D>(off_); }
+  T* range_begin() const { return p_ + off_; }   // stand-in only: first element of the accessed range
 
  private:
   T* p_ = nullptr;
-  size_t n_ = 0;
+  size_t n_ = 0, off_ = 0;
 };
 
 template <typename T, int D = 1>
@@ -491,11 +517,11 @@ class handler {
   template <typename Name, typename K>
   void parallel_for(nd_range<1> r, K kernel) { run(r, kernel, host_standin::kernels_use_barriers); }
   template <typename T, typename Acc>
-  void copy(const T* src, Acc dst) { std::memcpy(&dst[0], src, dst.size() * sizeof(T)); }
+  void copy(const T* src, Acc dst) { std::memcpy(dst.range_begin(), src, dst.size() * sizeof(T)); }
   template <typename Acc, typename T, typename = std::enable_if_t<!std::is_pointer<Acc>::value>>
-  void copy(Acc src, T* dst) { std::memcpy(dst, &src[0], src.size() * sizeof(T)); }
+  void copy(Acc src, T* dst) { std::memcpy(dst, src.range_begin(), src.size() * sizeof(T)); }
   template <typename Acc, typename T, typename = std::enable_if_t<!std::is_pointer<Acc>::value>>
-  void fill(Acc dst, const T& v) { for (size_t i = 0; i < dst.size(); ++i) dst[i] = v; }
+  void fill(Acc dst, const T& v) { for (size_t i = 0; i < dst.size(); ++i) dst.range_begin()[i] = v; }
   template <typename T>
   void fill(T* dst, const T& v, size_t n) { std::fill(dst, dst + n, v); }
   void memcpy(void* dst, const void* src, size_t n) { std::memcpy(dst, src, n); }
@@ -563,10 +589,17 @@ void handler::run(nd_range<1> r, const K& kernel, bool fibers) {
   if (err) std::rethrow_exception(err);
 }
 
-struct default_selector {};
-inline constexpr default_selector default_selector_v{};
-struct cpu_selector {};
-inline constexpr cpu_selector cpu_selector_v{};
+// selectors are callables scoring a device (SYCL 2020); there is one device here
+struct default_selector_t { int operator()(const device&) const { return 1; } };
+struct cpu_selector_t { int operator()(const device&) const { return 1; } };
+struct gpu_selector_t { int operator()(const device&) const { return -1; } };
+inline constexpr default_selector_t default_selector_v{};
+inline constexpr cpu_selector_t cpu_selector_v{};
+inline constexpr gpu_selector_t gpu_selector_v{};
+struct property_list {
+  template <typename... Ts>
+  property_list(Ts...) {}
+};
 namespace property {
 namespace queue {
 struct enable_profiling {};
@@ -587,13 +620,17 @@ class queue {
     cgf(h);
     return event();
   }
-  void wait() {}
-  void wait_and_throw() {}
+  void wait() const {}
+  void wait_and_throw() const {}
   device get_device() const { return device(); }
   context get_context() const { return context(); }
-  event memcpy(void* dst, const void* src, size_t n) { std::memcpy(dst, src, n); return event(); }
+  event memcpy(void* dst, const void* src, size_t n, const std::vector<event>& = {}) {
+    std::memcpy(dst, src, n);
+    return event();
+  }
   template <typename T>
-  event fill(T* p, const T& v, size_t n) { std::fill(p, p + n, v); return event(); }
+  event fill(T* p, const T& v, size_t n, const std::vector<event>& = {}) { std::fill(p, p + n, v); return event(); }
+  bool operator==(const queue&) const { return true; }
 };
 
 namespace usm {

@@ -365,3 +365,33 @@ def test_complex_gemm_of_the_reference(ref_libs):
     ref_host.gemm("t", "n", m, n, k, 1.0, A, k, B, k, 0.0, as_t, m)
     ox.cgemm("c", "n", m, n, k, 1.0, A, k, B, k, 0.0, blas_c, m, conj=True)
     assert np.array_equal(as_c, as_t) and np.abs(as_c - blas_c).max() > 1.0
+
+
+# binary -> (--gtest_filter, minimum number of tests): a bounded subset; the full runs (11 392 tests, all passing) are
+# recorded in profiles/r01/ref_host_unittests/
+HOST_UNITTESTS = {
+    "blas3_gemm_tall_skinny_test": ("*", 160),
+    "blas3_symm_test": ("*alloc_usm*", 480),
+    "blas3_gemm_test": ("*Small*:*AlphaZero*:*OffsetNonZero*alloc_usm*", 700),
+    "blas3_gemm_batched_test": ("*BetaNonZeroLDMatchFloat*", 100),
+    "blas3_trsm_test": ("*m_7__n_7_*:*m_16__n_16_*", 100),
+}
+
+
+@pytest.mark.parametrize("name", list(HOST_UNITTESTS))
+def test_reference_unit_tests_pass_on_the_host_stand_in(name):
+    """The executor behind "reference outputs" is checked with the reference's OWN tests: test/unittest/blas3/<name>.cpp
+    (unchanged) linked with the reference's own header-only library over oracle/sycl_host (`make -C oracle ref_tests`),
+    comparing with CBLAS through the reference's verifier."""
+    import subprocess
+    built = {p.name: p for p in ref_host.build_unittests()}
+    exe = built.get(f"ref_unittest_host_{name}")
+    if exe is None:
+        pytest.skip("oracle/_ref unit tests are not built and /root/reference is not present to build them")
+    flt, at_least = HOST_UNITTESTS[name]
+    r = subprocess.run([str(exe), f"--gtest_filter={flt}"], capture_output=True, text=True, timeout=900)
+    tail = "\n".join(r.stdout.splitlines()[-10:])
+    ran = [ln for ln in r.stdout.splitlines() if ln.startswith("[==========]")]
+    assert ran, tail + r.stderr[-2000:]
+    assert "[  FAILED  ]" not in r.stdout, tail
+    assert r.returncode == 0 and int(ran[-1].split()[1]) >= at_least, (r.returncode, ran[-1], tail)
