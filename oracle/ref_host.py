@@ -72,6 +72,18 @@ def build_unittests() -> list:
     return [unittest_path(t) for t in REF_TESTS if unittest_path(t).exists()]
 
 
+def build_bench() -> list:
+    """The reference's own bench_gemm and samples/gemm.cpp on its own library on the stand-in (`make -C oracle ref_bench`)."""
+    outs = [REF_DIR / "ref_bench_host_gemm", REF_DIR / "ref_sample_gemm_host"]
+    if (REFERENCE / "benchmark" / "portblas" / "main.cpp").exists():
+        newest = max(p.stat().st_mtime for p in [HERE / "Makefile", *(HERE / "sycl_host").rglob("*.hpp")])
+        if any(not o.exists() or o.stat().st_mtime < newest for o in outs):
+            r = subprocess.run(["make", "-C", str(HERE), "-j2", "-B", "ref_bench"], capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("reference benchmark (host) build failed:\n" + r.stdout[-3000:] + r.stderr[-3000:])
+    return [o for o in outs if o.exists()]
+
+
 def available(backend: str = "default") -> bool:
     return lib_path(backend).exists()
 

@@ -18,9 +18,11 @@
 
 #include <algorithm>
 #include <cassert>
+#include <chrono>
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <exception>
 #include <functional>
@@ -105,7 +107,12 @@ inline void barrier_yield();
 namespace host_standin {
 // Set to false by a caller that KNOWS the next kernels never reach a barrier (the no-local GEMMs): their work-items then
 // run as plain loop iterations instead of fibers.  A barrier reached in that mode aborts loudly.
-inline bool kernels_use_barriers = true;
+// (SYCL_HOST_STANDIN_NO_BARRIERS=1 in the environment sets the initial value to false: for the reference's own
+// benchmark executables, which cannot call into this header's knobs.)
+inline bool kernels_use_barriers = [] {
+  const char* e = std::getenv("SYCL_HOST_STANDIN_NO_BARRIERS");
+  return !(e != nullptr && e[0] == '1');
+}();
 }  // namespace host_standin
 
 // Declared so that the reference's non-GEMM headers parse; the GEMM path never executes them.
@@ -353,11 +360,20 @@ class device {
 
 class event {
  public:
+  event() = default;
+  event(uint64_t start_ns, uint64_t end_ns) : start_(start_ns), end_(end_ns) {}
   void wait() const {}
   void wait_and_throw() const {}
   static void wait(const std::vector<event>&) {}  // everything in this stand-in has completed when submit returns
+  // host wall-clock (steady_clock, ns) around the command group that produced the event
   template <typename P>
-  uint64_t get_profiling_info() const { return 0; }
+  uint64_t get_profiling_info() const {
+    if constexpr (std::is_same_v<P, info::event_profiling::command_end>) return end_;
+    else return start_;
+  }
+
+ private:
+  uint64_t start_ = 0, end_ = 0;
 };
 
 template <typename T, int D = 1, typename Alloc = void>
@@ -612,13 +628,20 @@ class context {};
 class queue {
  public:
   queue() = default;
-  template <typename... A>
-  explicit queue(A&&...) {}
+  template <typename Selector, typename = std::enable_if_t<!std::is_same_v<std::decay_t<Selector>, queue>>>
+  explicit queue(const Selector&, const property_list& = {}) {}
+  template <typename Selector, typename Handler, typename = std::enable_if_t<std::is_invocable_v<Handler, exception_list>>>
+  queue(const Selector&, Handler, const property_list& = {}) {}
   template <typename F>
   event submit(F&& cgf) {
+    const uint64_t t0 = now_ns();
     handler h;
     cgf(h);
-    return event();
+    return event(t0, now_ns());
+  }
+  static uint64_t now_ns() {
+    return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(
+               std::chrono::steady_clock::now().time_since_epoch()).count();
   }
   void wait() const {}
   void wait_and_throw() const {}

@@ -395,3 +395,29 @@ def test_reference_unit_tests_pass_on_the_host_stand_in(name):
     assert ran, tail + r.stderr[-2000:]
     assert "[  FAILED  ]" not in r.stdout, tail
     assert r.returncode == 0 and int(ran[-1].split()[1]) >= at_least, (r.returncode, ran[-1], tail)
+
+
+def test_reference_sample_and_benchmark_run_on_the_host_stand_in(tmp_path):
+    """BASELINE configs[0] names samples/gemm.cpp on the SYCL host CPU device: here the reference's sample and its
+    bench_gemm (BLAS_VERIFY_BENCHMARK on: each benchmark first checks its result against CBLAS) run on the reference's own
+    library over the host stand-in (`make -C oracle ref_bench`; cfg1 numbers: profiles/r01/ref_host_bench_gemm_cfg1.txt)."""
+    import json
+    import subprocess
+    built = {p.name: p for p in ref_host.build_bench()}
+    if len(built) < 2:
+        pytest.skip("oracle/_ref benchmark binaries are not built and /root/reference is not present to build them")
+    r = subprocess.run([str(built["ref_sample_gemm_host"])], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "C (after):" in r.stdout
+
+    def block(name, rows):
+        return np.array([[float(x) for x in ln.split()] for ln in r.stdout.split(name)[1].strip().splitlines()[:rows]])
+    A, B, C0, C1 = block("A:", 7), block("B:", 9), block("C (before):", 7), block("C (after):", 7)
+    assert np.allclose(C1, 1.5 * A @ B + 0.5 * C0, rtol=2e-3, atol=5e-2)   # the sample prints ~5 significant digits
+    csv = tmp_path / "p.csv"
+    csv.write_text("n,n,256,256,256,1,0\nt,n,127,65,33,1.5,0.5\n")
+    out = tmp_path / "r.json"
+    r = subprocess.run([str(built["ref_bench_host_gemm"]), "--csv-param", str(csv), "--benchmark_min_time=0.05",
+                        f"--benchmark_out={out}"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ERROR OCCURRED" not in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    rep = json.loads(out.read_text())["benchmarks"]
+    assert len(rep) == 8 and all("error_occurred" not in b and b["n_fl_ops"] > 0 for b in rep)   # 2 rows x {float, double} x {buffer, usm}
