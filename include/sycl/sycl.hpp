@@ -13,9 +13,11 @@
 //   malloc_device -> pbx_malloc
 #pragma once
 
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cassert>
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
@@ -393,6 +395,11 @@ class buffer {
 // as std::complex<T>, which is all the GEMM path needs
 namespace ext { namespace oneapi { namespace experimental {
 template <typename T> using complex = std::complex<T>;
+// joint_matrix fragment precision tag named by the reference's tf32 launcher call sites
+// (test/unittest/joint_matrix/joint_matrix_common.hpp); a type name only
+namespace matrix { namespace precision { class tf32 {}; } }
 } } }  // namespace ext::oneapi::experimental
+// sycl::ext::oneapi::bfloat16: the storage type of the bf16 GEMMs of this library
+namespace ext { namespace oneapi { using bfloat16 = __nv_bfloat16; } }
 
 }  // namespace sycl

@@ -11,6 +11,8 @@
                          (tests/cpp/shim/gtest/gtest.h), the reference's vendored cblas.h / clara.hpp and the
                          OpenBLAS of this image as the CBLAS the tests compare with
 
+  build/ref_unittest_joint_matrix_*  the REFERENCE's joint_matrix unit tests (test/unittest/joint_matrix/*.cpp), which call the
+                         path's seam blas::Gemm_Launcher<...>::_select_gemm directly (include/interface/gemm_launcher.h)
   build/ref_bench_*      the REFERENCE's own benchmark harness -- benchmark/portblas/main.cpp + benchmark/portblas/blas3/
                          {gemm,gemm_batched,gemm_batched_strided,symm,trsm}.cpp -- compiled UNCHANGED from
                          /root/reference with the definitions of benchmark/portblas/CMakeLists.txt:99-133
@@ -95,6 +97,44 @@ REF_BENCHMARKS = {
 }
 
 
+# the reference's joint_matrix unit tests (test/unittest/joint_matrix/CMakeLists.txt:41-52): they reach the GEMM path through
+# its seam, blas::Gemm_Launcher<...>::_select_gemm (launch_gemm.hpp), not through blas::_gemm
+REF_JOINT_MATRIX_TESTS = ["half_half_16_16_16", "half_half_32_8_16", "half_half_8_32_16", "half_float_16_16_16",
+                          "half_float_32_8_16", "half_float_8_32_16", "bfloat16_float_16_16_16", "bfloat16_float_32_8_16",
+                          "bfloat16_float_8_32_16", "tf32_float_16_16_8"]
+
+
+def build_reference_joint_matrix_tests() -> list:
+    """test/unittest/main.cpp + test/unittest/joint_matrix/<name>.cpp, unchanged, against include/ (whose
+    interface/gemm_launcher.h keeps the seam's full template signature) -> build/ref_unittest_joint_matrix_<name>."""
+    from concurrent.futures import ThreadPoolExecutor
+    openblas = sorted(SCIPY_LIBS.glob("libscipy_openblas*.so"))
+    jdir = REF / "test" / "unittest" / "joint_matrix"
+    if not (jdir / "launch_gemm.hpp").exists() or not openblas:
+        return []
+    shim = ROOT / "tests" / "cpp" / "shim"
+
+    def one(name: str) -> Path:
+        exe = OUT / f"ref_unittest_joint_matrix_{name}"
+        srcs = [REF / "test" / "unittest" / "main.cpp", jdir / f"{name}.cpp"]
+        newest = max(p.stat().st_mtime for p in [*srcs, *ROOT.glob("include/**/*.h*"), *shim.rglob("*.h"), HERE / "libpbx_gemm.so"])
+        if exe.exists() and exe.stat().st_mtime >= newest:
+            return exe
+        cmd = [CXX, "-std=c++17", "-O1", "-I", str(ROOT / "include"), "-I", "/usr/local/cuda/include", "-I", str(shim),
+               "-I", str(REF / "test"), "-I", str(jdir), "-I", str(REF / "common" / "include"),
+               "-I", str(REF / "external" / "cblas" / "include"), "-I", str(REF / "external" / "clara" / "include"),
+               "-include", str(shim / "cblas_scipy_rename.h"), "-DBLAS_INDEX_T=int", "-DBLAS_DATA_TYPE_DOUBLE",
+               "-DSB_ENABLE_USM", *[str(s) for s in srcs], "-o", str(exe), "-L", str(HERE), "-lpbx_gemm",
+               f"-Wl,-rpath,{HERE}", "-L", str(SCIPY_LIBS), f"-l:{openblas[0].name}", f"-Wl,-rpath,{SCIPY_LIBS}"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"reference joint_matrix test {name} does not build against include/:\n{r.stderr[-4000:]}")
+        return exe
+
+    with ThreadPoolExecutor(max_workers=5) as ex:
+        return list(ex.map(one, REF_JOINT_MATRIX_TESTS))
+
+
 def build_reference_benchmarks() -> list:
     """The reference's own benchmark executables (bench_gemm ...), unchanged, against this repository's headers and library."""
     openblas = sorted(SCIPY_LIBS.glob("libscipy_openblas*.so"))
@@ -139,6 +179,7 @@ def build() -> list:
         _compile(ref_src, exe, extra_inc=[REF / "samples"])
         built.append(exe)
     built += build_reference_unittests()
+    built += build_reference_joint_matrix_tests()
     built += build_reference_benchmarks()
     return built
 

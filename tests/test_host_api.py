@@ -57,6 +57,28 @@ def test_reference_unit_tests_compile_unchanged():
             "transb_n__alpha_1p50__beta_1p50__ldaMul_1__ldbMul_1__ldcMul_1__batchType_0") in r.stdout
 
 
+def test_reference_joint_matrix_tests_compile_against_the_seam():
+    """test/unittest/joint_matrix/*.cpp do not go through blas::_gemm: their launch_gemm.hpp instantiates the path's seam,
+    blas::Gemm_Launcher<containers..., WgSize, DoubleBuffer, ConflictA, ConflictB, ClSize, Tile<...>, TransA, TransB,
+    SymmA, SymmB, MemType, Algorithm, Vectorization, is_beta_zero, VectorSize, BatchType, UseJointMatrix>::_select_gemm
+    (reference include/interface/gemm_launcher.h:37-52).  include/interface/gemm_launcher.h keeps that signature, so the
+    ten tests compile UNCHANGED, link against libpbx_gemm.so and enumerate the reference's names."""
+    if not Path("/root/reference/test/unittest/joint_matrix/launch_gemm.hpp").exists():
+        pytest.skip("the reference tree is not present")
+    from portblas_b200 import build, build_host
+    build.build()
+    (ROOT / "build").mkdir(exist_ok=True)
+    built = build_host.build_reference_joint_matrix_tests()
+    assert len(built) == 10
+    for exe in built:
+        r = subprocess.run([str(exe), "--gtest_list_tests"], capture_output=True, text=True, timeout=120)
+        names = [ln for ln in r.stdout.splitlines() if ".test/" in ln]
+        assert len(names) >= 1500, (exe.name, len(names))
+    r = subprocess.run([str(ROOT / "build" / "ref_unittest_joint_matrix_tf32_float_16_16_8"), "--gtest_list_tests"],
+                       capture_output=True, text=True, timeout=120)
+    assert "JointMatrix/" in r.stdout and "tf32" in r.stdout
+
+
 def test_reference_benchmark_harness_compiles_unchanged():
     """The reference's OWN benchmark executables (benchmark/portblas/main.cpp + blas3/{gemm,gemm_batched,
     gemm_batched_strided,symm,trsm}.cpp with BLAS_VERIFY_BENCHMARK, half and complex as its CMake sets them) compile

@@ -54,6 +54,31 @@ def test_reference_unit_tests_pass_on_the_gpu(handle, name):
     assert r.returncode == 0 and n_ran >= at_least, (r.returncode, n_ran, tail)
 
 
+JOINT_MATRIX = ["half_half_16_16_16", "half_half_32_8_16", "half_half_8_32_16", "half_float_16_16_16", "half_float_32_8_16",
+                "half_float_8_32_16", "bfloat16_float_16_16_16", "bfloat16_float_32_8_16", "bfloat16_float_8_32_16",
+                "tf32_float_16_16_8"]
+
+
+@pytest.mark.xfail(strict=False, reason="built after the round-1 GPU budget was spent: first box run pending")
+@pytest.mark.parametrize("name", JOINT_MATRIX)
+def test_reference_joint_matrix_tests_pass_through_the_seam(handle, name):
+    """build/ref_unittest_joint_matrix_<name>: test/unittest/joint_matrix/<name>.cpp unchanged; it calls
+    blas::Gemm_Launcher<...>::_select_gemm (include/interface/gemm_launcher.h) with float storage whose low 13 / 16
+    mantissa bits are zero and compares with CBLAS.  USM containers (the buffer variants repeat the grid)."""
+    exe = ROOT / "build" / f"ref_unittest_joint_matrix_{name}"
+    if not exe.exists():
+        pytest.skip("reference joint_matrix tests were not prebuilt (needs /root/reference at build time)")
+    r = subprocess.run([str(exe), "--gtest_filter=*usm*"], capture_output=True, text=True, timeout=420)
+    tail = "\n".join(r.stdout.splitlines()[-15:])
+    out_dir = ROOT / "gpurun_out" / "ref_unittests"
+    out_dir.mkdir(parents=True, exist_ok=True)
+    (out_dir / f"joint_matrix_{name}.log").write_text(r.stdout[-200000:] + "\n--- stderr ---\n" + r.stderr[-20000:])
+    ran = [ln for ln in r.stdout.splitlines() if ln.startswith("[==========]")]
+    assert ran, tail + r.stderr[-2000:]
+    assert "[  FAILED  ]" not in r.stdout, tail
+    assert r.returncode == 0 and int(ran[-1].split()[1]) >= 700, (r.returncode, ran[-1], tail)
+
+
 # reference benchmark executable -> rows of its --csv-param file (benchmark/README.md: the column order per operator)
 BENCH_CSV = {
     "gemm": "n,n,1024,1024,1024,1.5,0.5\nt,n,512,333,257,1,0\nn,t,63,1025,129,1,1\n",
