@@ -68,7 +68,7 @@ def test_reference_joint_matrix_tests_pass_through_the_seam(handle, name):
     exe = ROOT / "build" / f"ref_unittest_joint_matrix_{name}"
     if not exe.exists():
         pytest.skip("reference joint_matrix tests were not prebuilt (needs /root/reference at build time)")
-    r = subprocess.run([str(exe), "--gtest_filter=*usm*"], capture_output=True, text=True, timeout=420)
+    r = subprocess.run([str(exe), "--gtest_filter=*usm*"], capture_output=True, text=True, timeout=180)
     tail = "\n".join(r.stdout.splitlines()[-15:])
     out_dir = ROOT / "gpurun_out" / "ref_unittests"
     out_dir.mkdir(parents=True, exist_ok=True)
