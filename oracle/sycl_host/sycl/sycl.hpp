@@ -7,7 +7,12 @@
 // `nd_item::barrier` switches between the work-items of the group (ucontext fibers), local accessors are a per-group
 // scratch array.  Work-groups are spread over OpenMP threads (they are independent by the SYCL execution model).
 //
-// What it is not: a SYCL implementation.  Only the names the GEMM path touches exist, in the shape that path needs.
+// How it is validated: the reference's own blas3 unit tests (test/unittest/blas3/*_test.cpp, float and double, USM and
+// buffer containers -- 11 392 tests), linked with the reference's own library over this header, all pass
+// (`make -C oracle ref_tests`, profiles/r01/ref_host_unittests/).
+//
+// What it is not: a SYCL implementation.  Only the names the reference's library touches exist, in the shape it needs;
+// group algorithms, sub-groups and atomics (BLAS-1/2 kernels) are declared so that the headers parse and abort if run.
 // Numerics it fixes: sycl::mad(a, b, c) is the fused multiply-add std::fma (what a CPU OpenCL device emits on an FMA
 // machine, and the choice oracle/gemm_oracle.c makes); sycl::half is the compiler's _Float16.
 //
@@ -296,13 +301,14 @@ template <typename T> inline T max(T a, T b) { return a < b ? b : a; }
 
 // ---------------------------------------------------------------- devices, events, queue
 namespace info {
+enum class local_mem_type { none, local, global };
 namespace device {
 struct name { using return_type = std::string; };
 struct vendor { using return_type = std::string; };
 struct max_compute_units { using return_type = unsigned; };
 struct max_work_group_size { using return_type = size_t; };
 struct local_mem_size { using return_type = size_t; };
-struct local_mem_type { using return_type = int; };
+struct local_mem_type { using return_type = info::local_mem_type; };
 struct sub_group_sizes { using return_type = std::vector<size_t>; };
 struct device_type;
 struct version { using return_type = std::string; };
@@ -315,12 +321,6 @@ struct device_type { using return_type = info::device_type; };
 namespace platform {
 struct name { using return_type = std::string; };
 }  // namespace platform
-namespace local_mem_type_ns {
-enum type : int { none = 0, local = 1, global = 2 };
-}
-struct local_mem_type {  // usable both as sycl::info::local_mem_type::local and as a value compared with an int
-  static constexpr int none = 0, local = 1, global = 2;
-};
 namespace event_profiling {
 struct command_submit { using return_type = uint64_t; };
 struct command_start { using return_type = uint64_t; };
