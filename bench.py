@@ -157,7 +157,7 @@ def _cpu_gemm():
     port of the kernel that backend picks (oracle/gemm_oracle.c -- bit-identical results, tests/test_oracle_ref.py).
     Returns (fn(ms, n, k, a, b, c), kind, cores, label)."""
     from oracle import oracle, ref_host
-    if ref_host.available("default"):
+    if ref_host.usable("default"):   # probed in a child process: a prebuilt library that cannot run here costs a fallback
         ref_host.set_fibers(False)
 
         def fn(ms, n, k, a, b, c):

@@ -88,6 +88,31 @@ def available(backend: str = "default") -> bool:
     return lib_path(backend).exists()
 
 
+_usable: dict = {}
+
+
+def usable(backend: str = "default") -> bool:
+    """available() AND the library loads and multiplies correctly on THIS machine -- probed once in a child process, so
+    that a prebuilt library that cannot run here (other CPU, missing runtime) costs a skip / a fallback, not the caller."""
+    if backend not in _usable:
+        ok = available(backend)
+        if ok:
+            import sys
+            code = ("import numpy as np; from oracle import ref_host as r; "
+                    "a = np.arange(1, 13, dtype=np.float32); b = np.arange(1, 13, dtype=np.float32)[::-1].copy(); "
+                    "c = np.zeros(9, dtype=np.float32); "
+                    f"r.gemm('n', 'n', 3, 3, 4, 1.0, a, 3, b, 4, 0.0, c, 3, backend={backend!r}); "
+                    "want = (a.reshape(4, 3).T @ b.reshape(3, 4).T).T.ravel(); "
+                    "raise SystemExit(0 if np.array_equal(c, want) else 3)")
+            try:
+                ok = subprocess.run([sys.executable, "-c", code], cwd=str(HERE.parent), capture_output=True,
+                                    timeout=120).returncode == 0
+            except Exception:
+                ok = False
+        _usable[backend] = ok
+    return _usable[backend]
+
+
 def lib(backend: str = "default") -> ctypes.CDLL:
     if backend not in _libs:
         if not available(backend):
