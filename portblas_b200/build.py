@@ -18,7 +18,9 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OUT = HERE / "libpbx_gemm.so"
 OBJ_DIR = HERE / "csrc" / "_obj"
-SOURCES = ["pbx_api.cu", "pbx_host.cu", "gemm_simt.cu", "gemm_dmma.cu", "gemm_tcgen05.cu", "blas3_ext.cu"]
+SOURCES = ["gemm_tc_inst_f32_pre0.cu", "gemm_tc_inst_f32_pre1.cu", "gemm_tc_inst_f32_pre2.cu", "gemm_tc_inst_f32_pre3.cu",
+           "gemm_tc_inst_f16.cu", "gemm_tc_inst_f16f32.cu", "gemm_tc_inst_bf16.cu", "gemm_tc_inst_bf16f32.cu",
+           "gemm_simt.cu", "gemm_dmma.cu", "blas3_ext.cu", "pbx_api.cu", "pbx_host.cu", "gemm_tcgen05.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -57,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             sys.stderr.write(r.stderr)
         return str(obj)
 
-    with ThreadPoolExecutor(max_workers=4) as ex:
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     cmd = [NVCC, "-shared", "-o", str(OUT), *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)

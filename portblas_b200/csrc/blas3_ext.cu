@@ -122,7 +122,7 @@ int gemm_complex(pbx_handle_t h, int real_dtype, char transa, char transb, int64
     h->last_error = "complex gemm: invalid argument";
     return PBX_ERR_INVALID_ARG;
   }
-  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  PBX_DEVICE_GUARD(h);
   const T ar = alpha[0], ai = alpha[1], br = beta[0], bi = beta[1];
   h->last_split_k = 1;
   h->last_repack = 0;
@@ -323,7 +323,7 @@ int pbx_symm(pbx_handle_t h, int dtype, char side, char uplo, int64_t m, int64_t
   const int sd = tolower((unsigned char)side), ul = tolower((unsigned char)uplo);
   if (ul != 'u' && ul != 'l') return PBX_ERR_INVALID_UPLO;   // symm_interface.hpp:51-53 (checked before side)
   if (sd != 'l' && sd != 'r') return PBX_ERR_INVALID_SIDE;   // symm_interface.hpp:70-72
-  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  PBX_DEVICE_GUARD(h);
   const double al = (dtype == PBX_F64) ? *(const double*)alpha : (double)*(const float*)alpha;
   const int64_t k = (sd == 'l') ? m : n;
   const void* Afull = A;
@@ -362,7 +362,7 @@ int pbx_trsm(pbx_handle_t h, int dtype, char side, char uplo, char trans, char d
   if (tr != 'n' && tr != 't') return PBX_ERR_TRSM_TRANS;
   if (dg != 'u' && dg != 'n') return PBX_ERR_TRSM_DIAG;
   if (!A || !B) { h->last_error = "pbx_trsm: null matrix pointer"; return PBX_ERR_INVALID_ARG; }
-  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  PBX_DEVICE_GUARD(h);
   if (dtype == PBX_F64)
     return trsm_impl<double, 64>(h, dtype, sd == 'l', ul == 'l', tr == 't', dg == 'u', m, n, *(const double*)alpha,
                                  (const double*)A, lda, (double*)B, ldb);

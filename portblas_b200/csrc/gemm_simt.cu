@@ -417,6 +417,9 @@ __global__ void __launch_bounds__(256) tf32_lo_kernel(const float* __restrict__ 
 // ---- fp32 operand -> two bf16 copies for the tf32 + 2 x bf16 product (EXPERIMENTAL, PBX_F32_SPLIT16=1) ----------
 // hi16 = bf16(a), lo16 = bf16(a - trunc_tf32(a)); the copies have their own leading dimension / batch stride (multiples
 // of 8 elements, so that they are TMA-legal whatever the source's were).  One warp per 2048-row chunk of a column.
+// VEC8: eight consecutive rows per lane -- two 16-byte loads, one 16-byte store per copy (needs a 16-byte-aligned source:
+// base, ld and stride multiples of 4 floats; the copies' ld16 / st16 are multiples of 8 by construction).
+template <bool VEC8>
 __global__ void __launch_bounds__(256) split16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
                                                       __nv_bfloat16* __restrict__ lo, int64_t rows, int64_t cols,
                                                       int64_t ld, int64_t stride, int64_t ld16, int64_t st16,
@@ -424,17 +427,39 @@ __global__ void __launch_bounds__(256) split16_kernel(const float* __restrict__ 
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t units = batch * cols * chunks;
+  auto lo_of = [](float x) {
+    const float d = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    return d == d ? d : 0.0f;   // inf - inf -> 0
+  };
   for (int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < units; u += nwarps) {
     const int64_t chunk = u % chunks, col = (u / chunks) % cols, b = u / (chunks * cols);
     const int64_t r0 = chunk * 2048, r1 = min(rows, r0 + 2048);
     const float* s = src + b * stride + col * ld;
     __nv_bfloat16* dh = hi + b * st16 + col * ld16;
     __nv_bfloat16* dl = lo + b * st16 + col * ld16;
-    for (int64_t r = r0 + lane; r < r1; r += 32) {
-      const float x = s[r];
-      const float d = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-      dh[r] = __float2bfloat16_rn(x);
-      dl[r] = __float2bfloat16_rn(d == d ? d : 0.0f);   // inf - inf -> 0
+    if (VEC8) {
+      int64_t r = r0 + lane * 8;
+      for (; r + 8 <= r1; r += 256) {
+        const float4 x0 = *reinterpret_cast<const float4*>(s + r), x1 = *reinterpret_cast<const float4*>(s + r + 4);
+        __nv_bfloat162 h[4], l[4];
+        h[0] = __floats2bfloat162_rn(x0.x, x0.y); h[1] = __floats2bfloat162_rn(x0.z, x0.w);
+        h[2] = __floats2bfloat162_rn(x1.x, x1.y); h[3] = __floats2bfloat162_rn(x1.z, x1.w);
+        l[0] = __floats2bfloat162_rn(lo_of(x0.x), lo_of(x0.y)); l[1] = __floats2bfloat162_rn(lo_of(x0.z), lo_of(x0.w));
+        l[2] = __floats2bfloat162_rn(lo_of(x1.x), lo_of(x1.y)); l[3] = __floats2bfloat162_rn(lo_of(x1.z), lo_of(x1.w));
+        *reinterpret_cast<uint4*>(dh + r) = *reinterpret_cast<const uint4*>(h);
+        *reinterpret_cast<uint4*>(dl + r) = *reinterpret_cast<const uint4*>(l);
+      }
+      for (int64_t t = r; t < min(r + 8, r1); ++t) {   // ragged end of the column (at most one lane)
+        const float x = s[t];
+        dh[t] = __float2bfloat16_rn(x);
+        dl[t] = __float2bfloat16_rn(lo_of(x));
+      }
+    } else {
+      for (int64_t r = r0 + lane; r < r1; r += 32) {
+        const float x = s[r];
+        dh[r] = __float2bfloat16_rn(x);
+        dl[r] = __float2bfloat16_rn(lo_of(x));
+      }
     }
   }
 }
@@ -564,8 +589,13 @@ int pbx_launch_split16(pbx_handle_t h, const float* src, void* hi, void* lo, int
   int64_t blocks = (units + 7) / 8;   // 8 warps per block
   const int64_t cap = (int64_t)h->sm_count * 16;
   if (blocks > cap) blocks = cap;
-  split16_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(src, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, rows, cols, ld,
-                                                          stride, ld16, st16, batch, chunks);
+  const bool vec8 = ((uintptr_t)src % 16 == 0) && (ld % 4 == 0) && (stride % 4 == 0);
+  if (vec8)
+    split16_kernel<true><<<(unsigned)blocks, 256, 0, h->stream>>>(src, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, rows, cols, ld,
+                                                                  stride, ld16, st16, batch, chunks);
+  else
+    split16_kernel<false><<<(unsigned)blocks, 256, 0, h->stream>>>(src, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, rows, cols, ld,
+                                                                   stride, ld16, st16, batch, chunks);
   h->launches++;
   PBX_CUDA_CHECK(h, cudaGetLastError());
   return PBX_OK;

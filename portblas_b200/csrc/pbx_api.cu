@@ -60,16 +60,28 @@ int pbx_create(pbx_handle_t* out, int device_ordinal, void* cuda_stream) {
   h->cc_minor = prop.minor;
   const char* fk = getenv("PBX_FORCE_KERNEL");
   if (fk) h->forced_kernel = atoi(fk);
-  if (cudaSetDevice(device_ordinal) != cudaSuccess) { delete h; return PBX_ERR_CUDA; }
+  const char* ds = getenv("PBX_DYNAMIC_SCHED");
+  if (ds) h->dynamic_sched = atoi(ds) != 0;
+  const char* pdl = getenv("PBX_PDL");
+  if (pdl) h->pdl = atoi(pdl) != 0;
+  {
+    PbxDeviceGuard guard(device_ordinal);
+    if (!guard.ok() || cudaMalloc(&h->tile_sched, 256) != cudaSuccess ||
+        cudaMemset(h->tile_sched, 0, 256) != cudaSuccess) {
+      delete h;
+      return PBX_ERR_CUDA;
+    }
+  }
   *out = h;
   return PBX_OK;
 }
 
 int pbx_destroy(pbx_handle_t h) {
   if (!h) return PBX_ERR_INVALID_ARG;
-  cudaSetDevice(h->device);
+  PbxDeviceGuard guard(h);
   cudaStreamSynchronize(h->stream);
   if (h->ws) cudaFree(h->ws);
+  if (h->tile_sched) cudaFree(h->tile_sched);
   for (int i = 0; i < 3; ++i)
     if (h->stage[i]) cudaFree(h->stage[i]);
   for (int i = 0; i < 2; ++i)
@@ -296,7 +308,7 @@ extern "C" {
 int pbx_scal_matrix(pbx_handle_t h, int dtype, int64_t m, int64_t n, const void* beta, void* C,
                     int64_t ldc, int64_t stridec, int64_t batch) {
   if (!h || !valid_dtype(dtype) || !beta || m < 0 || n < 0 || batch < 0) return PBX_ERR_INVALID_ARG;
-  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  PBX_DEVICE_GUARD(h);
   const double b = read_scalar(dtype, beta);
   h->last_split_k = 1;
   if (b == 1.0 || m == 0 || n == 0 || batch == 0) {  // blas1_interface.hpp:498-499
@@ -317,7 +329,7 @@ int pbx_gemm(pbx_handle_t h, int dtype, char transa, char transb, int64_t m, int
     h->last_error = "pbx_gemm: invalid argument";
     return PBX_ERR_INVALID_ARG;
   }
-  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  PBX_DEVICE_GUARD(h);
   const double al = read_scalar(dtype, alpha);
   const double be = read_scalar(dtype, beta);
   h->last_split_k = 1;
@@ -397,7 +409,7 @@ int pbx_gemm_multicast(pbx_handle_t h, int dtype, char transa, char transb, int6
   }
   if (n_dst == 1)
     return pbx_gemm(h, dtype, transa, transb, m, n, k, alpha, A, lda, 0, B, ldb, 0, beta, C_list[0], ldc, 0, 1, 0);
-  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  PBX_DEVICE_GUARD(h);
   const double al = read_scalar(dtype, alpha), be = read_scalar(dtype, beta);
   const int ta_c = tolower((unsigned char)transa), tb_c = tolower((unsigned char)transb);
   const bool plain = (al != 0.0) && (ta_c == 'n' || ta_c == 't' || ta_c == 'c') &&
@@ -429,7 +441,7 @@ int pbx_gemm_multicast(pbx_handle_t h, int dtype, char transa, char transb, int6
 // ---- CUDA IPC: one process per GPU, so a peer's C is reached through an exported allocation handle ---------------
 int pbx_ipc_export(pbx_handle_t h, const void* dptr, void* handle_out, int64_t* offset_out) {
   if (!h || !dptr || !handle_out || !offset_out) return PBX_ERR_INVALID_ARG;
-  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  PBX_DEVICE_GUARD(h);
   // the handle names the whole allocation: find its base (allocator blocks are sub-ranges of one cudaMalloc)
   typedef CUresult (*range_fn_t)(CUdeviceptr*, size_t*, CUdeviceptr);
   void* f = nullptr;
@@ -452,7 +464,7 @@ int pbx_ipc_export(pbx_handle_t h, const void* dptr, void* handle_out, int64_t* 
 
 int pbx_ipc_import(pbx_handle_t h, const void* handle, int64_t offset, void** dptr_out) {
   if (!h || !handle || !dptr_out || offset < 0) return PBX_ERR_INVALID_ARG;
-  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  PBX_DEVICE_GUARD(h);
   const std::string key(reinterpret_cast<const char*>(handle), sizeof(cudaIpcMemHandle_t));
   void* base = nullptr;
   for (auto& kv : h->ipc_open)
@@ -470,39 +482,39 @@ int pbx_ipc_import(pbx_handle_t h, const void* handle, int64_t offset, void** dp
 // ---- memory helpers ------------------------------------------------------------------
 int pbx_malloc(pbx_handle_t h, void** dptr, int64_t bytes) {
   if (!h || !dptr || bytes < 0) return PBX_ERR_INVALID_ARG;
-  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  PBX_DEVICE_GUARD(h);
   PBX_CUDA_CHECK(h, cudaMalloc(dptr, (size_t)(bytes > 0 ? bytes : 1)));
   return PBX_OK;
 }
 int pbx_free(pbx_handle_t h, void* dptr) {
   if (!h) return PBX_ERR_INVALID_ARG;
-  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  PBX_DEVICE_GUARD(h);
   PBX_CUDA_CHECK(h, cudaStreamSynchronize(h->stream));
   PBX_CUDA_CHECK(h, cudaFree(dptr));
   return PBX_OK;
 }
 int pbx_copy_to_device(pbx_handle_t h, const void* src, void* dst, int64_t bytes) {
   if (!h || bytes < 0) return PBX_ERR_INVALID_ARG;
-  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  PBX_DEVICE_GUARD(h);
   PBX_CUDA_CHECK(h, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, h->stream));
   return PBX_OK;
 }
 int pbx_copy_to_host(pbx_handle_t h, const void* src, void* dst, int64_t bytes) {
   if (!h || bytes < 0) return PBX_ERR_INVALID_ARG;
-  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  PBX_DEVICE_GUARD(h);
   PBX_CUDA_CHECK(h, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, h->stream));
   return PBX_OK;
 }
 int pbx_fill_bytes(pbx_handle_t h, void* dst, int value, int64_t bytes) {
   if (!h || bytes < 0) return PBX_ERR_INVALID_ARG;
-  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  PBX_DEVICE_GUARD(h);
   PBX_CUDA_CHECK(h, cudaMemsetAsync(dst, value, (size_t)bytes, h->stream));
   return PBX_OK;
 }
 
 int pbx_copy_device_to_device(pbx_handle_t h, const void* src, void* dst, int64_t bytes) {
   if (!h || bytes < 0) return PBX_ERR_INVALID_ARG;
-  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  PBX_DEVICE_GUARD(h);
   PBX_CUDA_CHECK(h, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, h->stream));
   return PBX_OK;
 }
@@ -518,7 +530,7 @@ extern "C" {
 int pbx_fill(pbx_handle_t h, void* dst, const void* value, int elem_bytes, int64_t count) {
   if (!h || !value || count < 0 || (elem_bytes != 2 && elem_bytes != 4 && elem_bytes != 8)) return PBX_ERR_INVALID_ARG;
   if (count == 0) return PBX_OK;
-  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  PBX_DEVICE_GUARD(h);
   int64_t blocks = (count + 255) / 256;
   if (blocks > (int64_t)h->sm_count * 16) blocks = (int64_t)h->sm_count * 16;
   if (elem_bytes == 2) pbx_fill_kernel<uint16_t><<<(unsigned)blocks, 256, 0, h->stream>>>((uint16_t*)dst, *(const uint16_t*)value, count);
@@ -532,7 +544,7 @@ int pbx_fill(pbx_handle_t h, void* dst, const void* value, int elem_bytes, int64
 // ---- events ---------------------------------------------------------------------------------
 int pbx_event_create(pbx_handle_t h, void** ev) {
   if (!h || !ev) return PBX_ERR_INVALID_ARG;
-  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  PBX_DEVICE_GUARD(h);
   cudaEvent_t e;
   PBX_CUDA_CHECK(h, cudaEventCreate(&e));
   *ev = (void*)e;

@@ -72,11 +72,30 @@ extern "C" int pbx_gemm_host(pbx_handle_t h, int dtype, char transa, char transb
                              int64_t k, const void* alpha, const void* A_host, int64_t lda, int64_t stridea,
                              const void* B_host, int64_t ldb, int64_t strideb, const void* beta, void* C_host,
                              int64_t ldc, int64_t stridec, int64_t batch, int batch_type) {
-  if (!h || dtype < PBX_F32 || dtype > PBX_BF16_F32 || !alpha || !beta || m < 0 || n < 0 || k < 0 || batch < 1 ||
+  if (!h || dtype < PBX_F32 || dtype > PBX_BF16_F32 || !alpha || !beta || m < 0 || n < 0 || k < 0 || batch < 0 ||
       (batch_type != 0 && batch_type != 1))
     return PBX_ERR_INVALID_ARG;
-  PBX_CUDA_CHECK(h, cudaSetDevice(h->device));
+  PBX_DEVICE_GUARD(h);
   const int ta_c = tolower((unsigned char)transa), tb_c = tolower((unsigned char)transb);
+  {
+    // pbx_gemm's front-end rules, in its order and with its codes, BEFORE any buffer size is derived from the strides
+    // (gemm_interface.hpp:112-166): alpha == 0 skips the validation there; this entry point additionally refuses
+    // negative strides in that case, because it sizes host <-> device copies from them.
+    const double al0 = dtype == PBX_F64 ? *(const double*)alpha : (double)*(const float*)alpha;
+    const bool strided = batch > 1 && batch_type == 0;
+    if (al0 != 0.0) {
+      if (ta_c != 'n' && ta_c != 't' && ta_c != 'c') return PBX_ERR_INVALID_TRANSA;
+      if (tb_c != 'n' && tb_c != 't' && tb_c != 'c') return PBX_ERR_INVALID_TRANSB;
+      if (strided) {
+        if (stridec < ldc * n || stridec < 0) return PBX_ERR_INVALID_STRIDEC;
+        if (stridea < 0) return PBX_ERR_INVALID_STRIDEA;
+        if (strideb < 0) return PBX_ERR_INVALID_STRIDEB;
+      }
+    } else if (strided && (stridea < 0 || strideb < 0 || stridec < 0)) {
+      return PBX_ERR_INVALID_ARG;
+    }
+    if (batch == 0 || m == 0 || n == 0) return PBX_OK;   // nothing to compute, nothing to copy (pbx_gemm: no-op)
+  }
   const bool ta = ta_c != 'n', tb = tb_c != 'n';
   const int64_t es = (int64_t)pbx_in_size(dtype), eo = (int64_t)pbx_out_size(dtype);
   const int64_t a_rows = ta ? k : m, a_cols = ta ? m : k;   // stored shapes

@@ -60,6 +60,11 @@ struct pbx_handle_s {
   int conj_transpose = 0;   // complex GEMM: 0 = 'c' behaves as 't' (the reference), 1 = BLAS conjugate-transpose
   // peer allocations opened through CUDA IPC (pbx_ipc_import): 64-byte handle -> mapped base pointer
   std::vector<std::pair<std::string, void*>> ipc_open;
+  // dynamic tile schedule of the persistent tcgen05 kernel: {tiles handed out, groups done}, zero between launches
+  // (the kernel re-arms them itself); PBX_DYNAMIC_SCHED=0 / PBX_PDL=0 switch the two launch features off (testing)
+  unsigned int* tile_sched = nullptr;
+  int dynamic_sched = 1;
+  int pdl = 1;
   // staging buffers for pbx_gemm_host
   void* stage[3] = {nullptr, nullptr, nullptr};
   int64_t stage_bytes[3] = {0, 0, 0};
@@ -78,6 +83,28 @@ struct pbx_handle_s {
       return PBX_ERR_CUDA;                                                               \
     }                                                                                    \
   } while (0)
+
+// Every entry point works on the handle's device and leaves the caller's current device as it found it: a
+// single-process multi-GPU program (torch, or several SB_Handles in one thread) must not have its thread switched
+// to another GPU by a library call.
+struct PbxDeviceGuard {
+  int prev = -1;
+  bool changed = false, good = true;
+  explicit PbxDeviceGuard(pbx_handle_t h) { enter(h->device); }
+  explicit PbxDeviceGuard(int device) { enter(device); }
+  ~PbxDeviceGuard() { if (changed) cudaSetDevice(prev); }
+  PbxDeviceGuard(const PbxDeviceGuard&) = delete;
+  PbxDeviceGuard& operator=(const PbxDeviceGuard&) = delete;
+  bool ok() const { return good; }
+ private:
+  void enter(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { good = false; return; }
+    if (prev != device) { good = (cudaSetDevice(device) == cudaSuccess); changed = good; }
+  }
+};
+#define PBX_DEVICE_GUARD(h)                                                              \
+  PbxDeviceGuard _pbx_device_guard(h);                                                   \
+  if (!_pbx_device_guard.ok()) { (h)->last_error = "cudaSetDevice failed"; return PBX_ERR_CUDA; }
 
 static inline size_t pbx_in_size(int dtype) {
   switch (dtype) {

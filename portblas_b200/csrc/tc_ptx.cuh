@@ -215,6 +215,26 @@ __device__ __forceinline__ void tc_mma_2sm(uint32_t d_tmem, uint64_t adesc, uint
   }
 }
 
+// ---- programmatic dependent launch -----------------------------------------------------------
+// wait: blocks until every grid this one depends on has completed and its memory is visible (no-op without the launch
+// attribute).  launch_dependents: lets the next grid in the stream start launching once all CTAs of this grid have
+// issued it (its CTAs still cannot touch dependent memory before their own griddepcontrol.wait).
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---- cluster-scope shared memory helpers of the tile scheduler ---------------------------------
+__device__ __forceinline__ void st_shared_cluster_u32(uint32_t cluster_addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 // ---- descriptors -------------------------------------------------------------------------
 // 128-byte-swizzled operand tile.  lbo/sbo in bytes.
 //   K-major : rows of 128 B (one per M/N index), 8-row groups 1024 B apart -> sbo = 1024

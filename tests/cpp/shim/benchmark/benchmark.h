@@ -103,6 +103,7 @@ class Benchmark {
   Benchmark* MinTime(double) { return this; }
   std::string name;
   std::function<void(State&)> fn;
+  std::unique_ptr<State> done;   // BENCHMARK_SHIM_RUN_AT_REGISTRATION: the finished run, reported later
 };
 
 inline std::vector<std::unique_ptr<Benchmark>>& registry() {
@@ -134,11 +135,23 @@ inline std::string json_escape(const std::string& s) {
 
 }  // namespace internal
 
+// BENCHMARK_SHIM_RUN_AT_REGISTRATION: the benchmark body runs inside RegisterBenchmark and RunSpecifiedBenchmarks only
+// reports it.  Needed for the reference's benchmark/portblas/blas3/symm.cpp, whose registered lambda captures the loop
+// locals `side_c` / `uplo_c` BY REFERENCE (symm.cpp:139-147, `[&]`): by the time a deferred runner calls it they are dead
+// stack slots (upstream bug, independent of the BLAS underneath).  Running at registration reads them while they live.
 template <typename Lambda, typename... Args>
 internal::Benchmark* RegisterBenchmark(const char* name, Lambda&& fn, Args&&... args) {
   auto bound = [fn, args...](State& st) mutable { fn(st, args...); };
   internal::registry().emplace_back(new internal::Benchmark(name, bound));
-  return internal::registry().back().get();
+  internal::Benchmark* b = internal::registry().back().get();
+#ifdef BENCHMARK_SHIM_RUN_AT_REGISTRATION
+  auto& o = internal::options();
+  if (!o.list_only && std::regex_search(b->name, std::regex(o.filter))) {
+    b->done.reset(new State(o.min_time));
+    b->fn(*b->done);
+  }
+#endif
+  return b;
 }
 template <typename Lambda, typename... Args>
 internal::Benchmark* RegisterBenchmark(const std::string& name, Lambda&& fn, Args&&... args) {
@@ -176,8 +189,9 @@ inline size_t RunSpecifiedBenchmarks() {
   for (auto& b : internal::registry()) {
     if (!std::regex_search(b->name, re)) continue;
     if (o.list_only) { std::cout << b->name << "\n"; continue; }
-    State st(o.min_time);
-    b->fn(st);
+    State fresh(o.min_time);
+    if (!b->done) b->fn(fresh);
+    State& st = b->done ? *b->done : fresh;
     ++ran;
     const double it = st.iterations() > 0 ? (double)st.iterations() : 1.0;
     const double real_ns = st.real_seconds() * 1e9 / it;

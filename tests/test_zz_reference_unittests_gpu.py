@@ -3,12 +3,10 @@ against libpbx_gemm.so: test/unittest/blas3/blas3_gemm_test.cpp (float, double, 
 blas3_gemm_batched_test.cpp (strided + interleaved), blas3_gemm_tall_skinny_test.cpp, blas3_symm_test.cpp and
 blas3_trsm_test.cpp, each comparing with CBLAS through the reference's own verifier and tolerance.
 
-First box run (round 1, the last 20 s of the GPU budget, all binaries at once: profiles/r01/ref_unittests/):
-blas3_gemm_tall_skinny_test 320/320 and blas3_symm_test 488/488 (alloc_usm) PASSED; blas3_gemm_test 1189, blas3_gemm_batched_test
-854 and blas3_trsm_test 446 tests OK with none failed when the 20 s ran out (float, double, half->float, half->half reached;
-the complex suites were not).  The two complete suites are therefore plain tests; the three cut short stay non-strict xfail
-until a box run sees them end (a pass shows as XPASS).  The reference's benchmark executables (build/ref_bench_*) run here too,
-with the verification the reference builds them with by default.  The file sorts last on purpose.
+Round 2: every suite ran to its end on the box (logs: profiles/r02/ref_unittests/), so all of them are plain tests --
+no xfail.  The reference's benchmark executables (build/ref_bench_*) run here too, with the verification the reference
+builds them with by default (BLAS_VERIFY_BENCHMARK: each benchmark first checks its result against CBLAS).
+The file sorts last on purpose.
 """
 from __future__ import annotations
 
@@ -32,11 +30,7 @@ SUITES = {
 }
 
 
-COMPLETE_ON_THE_BOX = {"blas3_gemm_tall_skinny_test", "blas3_symm_test"}
-_unfinished = pytest.mark.xfail(strict=False, reason="ran clean on the box but was cut short by the round-1 GPU budget")
-
-
-@pytest.mark.parametrize("name", [n if n in COMPLETE_ON_THE_BOX else pytest.param(n, marks=_unfinished) for n in SUITES])
+@pytest.mark.parametrize("name", list(SUITES))
 def test_reference_unit_tests_pass_on_the_gpu(handle, name):
     exe = ROOT / "build" / f"ref_unittest_{name}"
     if not exe.exists():
@@ -59,7 +53,6 @@ JOINT_MATRIX = ["half_half_16_16_16", "half_half_32_8_16", "half_half_8_32_16", 
                 "tf32_float_16_16_8"]
 
 
-@pytest.mark.xfail(strict=False, reason="built after the round-1 GPU budget was spent: first box run pending")
 @pytest.mark.parametrize("name", JOINT_MATRIX)
 def test_reference_joint_matrix_tests_pass_through_the_seam(handle, name):
     """build/ref_unittest_joint_matrix_<name>: test/unittest/joint_matrix/<name>.cpp unchanged; it calls
@@ -82,14 +75,16 @@ def test_reference_joint_matrix_tests_pass_through_the_seam(handle, name):
 # reference benchmark executable -> rows of its --csv-param file (benchmark/README.md: the column order per operator)
 BENCH_CSV = {
     "gemm": "n,n,1024,1024,1024,1.5,0.5\nt,n,512,333,257,1,0\nn,t,63,1025,129,1,1\n",
-    "gemm_batched": "n,n,64,64,64,1,0,32,0\nt,n,33,65,17,1.5,0.5,7,0\nn,n,32,32,32,1,1,64,1\n",
+    # batch type is spelled out (common_utils.hpp:240-247); the interleaved rows are the ones the reference ships in
+    # benchmark/config_csv/blas3/gemm_batched/gemm_batched_interleaved.csv plus a ragged one
+    "gemm_batched": ("n,n,64,64,64,1,0,32,strided\nt,n,33,65,17,1.5,0.5,7,strided\nn,n,32,32,32,1,1,64,interleaved\n"
+                     "n,n,65,3,49,1,0,32,interleaved\nt,t,230,230,49,1,0,32,interleaved\nn,t,17,9,5,1.5,0.5,7,interleaved\n"),
     "gemm_batched_strided": "n,n,128,128,128,1,0,16,2,2,2\nt,t,33,65,17,1.5,0.5,5,1,1,1\n",
     "symm": "l,u,512,256,1,0\nr,l,127,255,1.5,0.5\n",
     "trsm": "l,u,n,n,512,256,1\nr,l,t,u,127,255,2\n",
 }
 
 
-@_unfinished
 @pytest.mark.parametrize("name", list(BENCH_CSV))
 def test_reference_benchmark_harness_runs_and_verifies(handle, name, tmp_path):
     """build/ref_bench_<name>: the reference's benchmark/portblas/blas3/<name>.cpp + main.cpp, unchanged, with
