@@ -109,7 +109,7 @@ int pbx_set_split_k(pbx_handle_t h, int slices /* 0 = auto, 1 = never, >1 = forc
 int pbx_last_kernel(pbx_handle_t h);               /* pbx_kernel_t used by the last call */
 int pbx_last_split_k(pbx_handle_t h);              /* K slices used by the last call */
 int pbx_last_repack(pbx_handle_t h);               /* bit 0 / 1: A / B was re-laid out to a 16-byte-legal copy */
-int pbx_last_presplit(pbx_handle_t h);             /* fp32 mode of the last call: 0 in-kernel 3xTF32 split, 1 pre-split lo halves, 2 single tf32 (SB_ENABLE_JOINT_MATRIX=1) */
+int pbx_last_presplit(pbx_handle_t h);             /* fp32 mode of the last call: 0 in-kernel 3xTF32 split, 1 pre-split tf32 lo halves, 2 single tf32 (SB_ENABLE_JOINT_MATRIX=1), 3 tf32 + 2 x bf16 (pre-split bf16 copies) */
 int64_t pbx_launch_count(pbx_handle_t h);          /* kernels launched through this handle so far */
 int64_t pbx_workspace_bytes(pbx_handle_t h);       /* current size of the pooled workspace */
 /* The tensor-core tile plan for a shape as a pure function (no device, no handle): CTA group (1 or 2), tile width,
@@ -218,6 +218,39 @@ int pbx_gemm_multicast(pbx_handle_t h, int dtype, char transa, char transb, int6
                        void* const* C_list, int n_dst, int64_t ldc);
 int pbx_ipc_export(pbx_handle_t h, const void* dptr, void* handle_out /* 64 bytes */, int64_t* offset_out);
 int pbx_ipc_import(pbx_handle_t h, const void* handle /* 64 bytes */, int64_t offset, void** dptr_out);
+
+/* ---- multi-GPU from one host thread: a group of devices with peer access ----------------------------------------
+ * The reference has no multi-device code (one SB_Handle == one sycl::queue, include/sb_handle/portblas_handle.h:51-60);
+ * these entry points are the north star's "large square GEMMs are partitioned by M-blocks and strided-batched GEMMs by
+ * batch across the 8 GPUs of one box" for a C / C++ caller (samples/gemm_multi_b200.cpp).  A group owns one handle and
+ * one stream per device; every call is asynchronous on those streams, pbx_multi_synchronize waits for all of them.
+ * pbx_shard_range is THE partition (pure function, also bound by portblas_b200/sharding.py): part `index` of `parts`
+ * gets [start, start+count) of `total` units, shares are multiples of `align` (M-blocks: 256 rows; batches: 1).     */
+typedef struct pbx_multi_s* pbx_multi_t;
+int pbx_shard_range(int64_t total, int parts, int index, int64_t align, int64_t* start, int64_t* count);
+int pbx_multi_create(pbx_multi_t* out, int n_dev, const int* device_ordinals /* NULL = 0..n_dev-1 */);
+int pbx_multi_destroy(pbx_multi_t mh);
+int pbx_multi_device_count(pbx_multi_t mh);
+pbx_handle_t pbx_multi_handle(pbx_multi_t mh, int i);   /* device i's handle (its stream: pbx_get_stream) */
+int pbx_multi_synchronize(pbx_multi_t mh);
+const char* pbx_multi_last_error(pbx_multi_t mh);
+/* C <- alpha*op(A)*op(B) + beta*C, M-block sharded, operands resident: A_blocks[g] = device g's rows
+ * pbx_shard_range(m, G, g, 256) of op(A) (leading dimension lda), B_full[g] = all of B on device g, C_full[g] = device
+ * g's m x n C.  gather == 0: device g writes its rows of its own C.  gather != 0: the GEMM epilogue of every device
+ * stores its tiles into ALL devices' C over NVLink, so each device ends with the whole product (no collective).  */
+int pbx_gemm_sharded(pbx_multi_t mh, int dtype, char transa, char transb, int64_t m, int64_t n, int64_t k,
+                     const void* alpha, const void* const* A_blocks, int64_t lda, const void* const* B_full, int64_t ldb,
+                     const void* beta, void* const* C_full, int64_t ldc, int gather);
+/* strided batches cut into batch ranges pbx_shard_range(batch, G, g, 1); X_shards[g] = first entry device g owns */
+int pbx_gemm_strided_batched_sharded(pbx_multi_t mh, int dtype, char transa, char transb, int64_t m, int64_t n, int64_t k,
+                                     const void* alpha, const void* const* A_shards, int64_t lda, int64_t stridea,
+                                     const void* const* B_shards, int64_t ldb, int64_t strideb, const void* beta,
+                                     void* const* C_shards, int64_t ldc, int64_t stridec, int64_t batch);
+/* blas::_gemm on HOST operands over the whole group (synchronous): every device uploads its M-block of A and 1/G of
+ * B, the B panels are exchanged over NVLink, every device computes and downloads its block of C.                 */
+int pbx_gemm_sharded_host(pbx_multi_t mh, int dtype, char transa, char transb, int64_t m, int64_t n, int64_t k,
+                          const void* alpha, const void* A_host, int64_t lda, const void* B_host, int64_t ldb,
+                          const void* beta, void* C_host, int64_t ldc);
 
 /* ---- host-buffer convenience path (used for the end-to-end metric) -------
  * Same semantics as pbx_gemm, but A, B, C are HOST pointers (ideally pinned):

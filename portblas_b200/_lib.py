@@ -63,6 +63,20 @@ SYMBOLS = {
     "pbx_ipc_export": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int64)]),
     "pbx_ipc_import": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_void_p)]),
     "pbx_gemm_host": (c_int, [c_void_p, c_int, c_char, c_char] + _GEMM_TAIL),
+    "pbx_shard_range": (c_int, [c_int64, c_int, c_int, c_int64, POINTER(c_int64), POINTER(c_int64)]),
+    "pbx_multi_create": (c_int, [POINTER(c_void_p), c_int, POINTER(c_int)]),
+    "pbx_multi_destroy": (c_int, [c_void_p]),
+    "pbx_multi_device_count": (c_int, [c_void_p]),
+    "pbx_multi_handle": (c_void_p, [c_void_p, c_int]),
+    "pbx_multi_synchronize": (c_int, [c_void_p]),
+    "pbx_multi_last_error": (c_char_p, [c_void_p]),
+    "pbx_gemm_sharded": (c_int, [c_void_p, c_int, c_char, c_char, c_int64, c_int64, c_int64, c_void_p, POINTER(c_void_p), c_int64,
+                                 POINTER(c_void_p), c_int64, c_void_p, POINTER(c_void_p), c_int64, c_int]),
+    "pbx_gemm_strided_batched_sharded": (c_int, [c_void_p, c_int, c_char, c_char, c_int64, c_int64, c_int64, c_void_p,
+                                                 POINTER(c_void_p), c_int64, c_int64, POINTER(c_void_p), c_int64, c_int64,
+                                                 c_void_p, POINTER(c_void_p), c_int64, c_int64, c_int64]),
+    "pbx_gemm_sharded_host": (c_int, [c_void_p, c_int, c_char, c_char, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64,
+                                      c_void_p, c_int64, c_void_p, c_void_p, c_int64]),
     "pbx_malloc": (c_int, [c_void_p, POINTER(c_void_p), c_int64]),
     "pbx_free": (c_int, [c_void_p, c_void_p]),
     "pbx_copy_to_device": (c_int, [c_void_p, c_void_p, c_void_p, c_int64]),

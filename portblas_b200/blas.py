@@ -287,3 +287,80 @@ def _gemm_multicast(sb_handle: SB_Handle, _TransA, _TransB, _M, _N, _K, _alpha, 
         ctypes.c_void_p(b_.data_ptr()), int(_ldb), ctypes.cast(ctypes.pointer(be), ctypes.c_void_p), arr, len(c_ptrs),
         int(_ldc))
     _check(sb_handle, st)
+
+
+# ---- multi-GPU from one process: include/pbx_gemm.h pbx_multi_* / pbx_gemm_sharded* (C++ mirror: blas::multi) -------
+class SB_Handle_Group:
+    """A group of devices with peer access, one handle and one stream each (no reference counterpart: a
+    blas::SB_Handle is one sycl::queue, include/sb_handle/portblas_handle.h:51-60).  ``devices`` may repeat an ordinal
+    (several shards on one GPU)."""
+
+    def __init__(self, devices):
+        self._lib = _lib.load()
+        self._mh = ctypes.c_void_p()
+        devs = [int(d) for d in devices]
+        arr = (ctypes.c_int * len(devs))(*devs)
+        st = self._lib.pbx_multi_create(ctypes.byref(self._mh), len(devs), arr)
+        if st != _lib.OK:
+            self._mh = None
+            raise PbxError(self._lib.pbx_status_string(st).decode())
+        self.devices = devs
+
+    def close(self) -> None:
+        if getattr(self, "_mh", None):
+            self._lib.pbx_multi_destroy(self._mh)
+            self._mh = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self) -> int:
+        return self._lib.pbx_multi_device_count(self._mh)
+
+    def wait(self) -> None:
+        self._check(self._lib.pbx_multi_synchronize(self._mh))
+
+    def _check(self, status: int) -> None:
+        if status == _lib.OK:
+            return
+        text = self._lib.pbx_status_string(status).decode()
+        if 1 <= status <= 5:
+            raise ValueError(text)
+        raise PbxError(f"{text}: {self._lib.pbx_multi_last_error(self._mh).decode()}")
+
+    def _ptrs(self, tensors):
+        return (ctypes.c_void_p * len(tensors))(*[ctypes.c_void_p(t.data_ptr()) for t in tensors])
+
+    def gemm_sharded(self, transa, transb, m, n, k, alpha, a_blocks, lda, b_full, ldb, beta, c_full, ldc, gather=True) -> None:
+        """M-block sharded ``_gemm``: ``a_blocks[g]`` = device g's rows ``sharding.split_range(m, G, g, 256)`` of op(A),
+        ``b_full[g]`` = all of B on device g, ``c_full[g]`` = device g's m x n C.  Asynchronous (``wait()``)."""
+        dt = _dtype_of(a_blocks[0], b_full[0], c_full[0])
+        al, be = _scalar(dt, float(alpha)), _scalar(dt, float(beta))
+        self._check(self._lib.pbx_gemm_sharded(
+            self._mh, dt, str(transa).encode()[:1], str(transb).encode()[:1], int(m), int(n), int(k),
+            ctypes.cast(ctypes.pointer(al), ctypes.c_void_p), self._ptrs(a_blocks), int(lda), self._ptrs(b_full), int(ldb),
+            ctypes.cast(ctypes.pointer(be), ctypes.c_void_p), self._ptrs(c_full), int(ldc), int(bool(gather))))
+
+    def gemm_strided_batched_sharded(self, transa, transb, m, n, k, alpha, a_shards, lda, stridea, b_shards, ldb, strideb, beta,
+                                     c_shards, ldc, stridec, batch_size) -> None:
+        """Batch-range sharded ``_gemm_strided_batched``: ``x_shards[g]`` starts at the first entry device g owns."""
+        dt = _dtype_of(a_shards[0], b_shards[0], c_shards[0])
+        al, be = _scalar(dt, float(alpha)), _scalar(dt, float(beta))
+        self._check(self._lib.pbx_gemm_strided_batched_sharded(
+            self._mh, dt, str(transa).encode()[:1], str(transb).encode()[:1], int(m), int(n), int(k),
+            ctypes.cast(ctypes.pointer(al), ctypes.c_void_p), self._ptrs(a_shards), int(lda), int(stridea), self._ptrs(b_shards),
+            int(ldb), int(strideb), ctypes.cast(ctypes.pointer(be), ctypes.c_void_p), self._ptrs(c_shards), int(ldc),
+            int(stridec), int(batch_size)))
+
+    def gemm_sharded_host(self, transa, transb, m, n, k, alpha, a_host, lda, b_host, ldb, beta, c_host, ldc) -> None:
+        """``_gemm`` on HOST tensors over the whole group (synchronous)."""
+        dt = _dtype_of(a_host, b_host, c_host)
+        al, be = _scalar(dt, float(alpha)), _scalar(dt, float(beta))
+        self._check(self._lib.pbx_gemm_sharded_host(
+            self._mh, dt, str(transa).encode()[:1], str(transb).encode()[:1], int(m), int(n), int(k),
+            ctypes.cast(ctypes.pointer(al), ctypes.c_void_p), ctypes.c_void_p(a_host.data_ptr()), int(lda),
+            ctypes.c_void_p(b_host.data_ptr()), int(ldb), ctypes.cast(ctypes.pointer(be), ctypes.c_void_p),
+            ctypes.c_void_p(c_host.data_ptr()), int(ldc)))

@@ -18,9 +18,9 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OUT = HERE / "libpbx_gemm.so"
 OBJ_DIR = HERE / "csrc" / "_obj"
-SOURCES = ["gemm_tc_inst_f32_pre0.cu", "gemm_tc_inst_f32_pre1.cu", "gemm_tc_inst_f32_pre2.cu", "gemm_tc_inst_f32_pre3.cu",
+SOURCES = ["gemm_tc_inst_f32_pre0.cu", "gemm_tc_inst_f32_pre1.cu", "gemm_tc_inst_f32_pre2.cu", "gemm_tc_inst_f32_pre3.cu", "gemm_tc_inst_f32_pre4.cu",
            "gemm_tc_inst_f16.cu", "gemm_tc_inst_f16f32.cu", "gemm_tc_inst_bf16.cu", "gemm_tc_inst_bf16f32.cu",
-           "gemm_simt.cu", "gemm_dmma.cu", "blas3_ext.cu", "pbx_api.cu", "pbx_host.cu", "gemm_tcgen05.cu"]
+           "gemm_simt.cu", "gemm_dmma.cu", "blas3_ext.cu", "pbx_api.cu", "pbx_host.cu", "pbx_multi.cu", "gemm_tcgen05.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -1,6 +1,7 @@
 """Build the C++ host-API callers against include/ + libpbx_gemm.so (plain g++, no nvcc):
 
   build/gemm_b200        samples/gemm_b200.cpp (this repo's own caller / self-check)
+  build/gemm_multi_b200  samples/gemm_multi_b200.cpp (one SGEMM over all B200s of the box through blas::multi)
   build/ref_sample_gemm  the REFERENCE's samples/gemm.cpp compiled UNCHANGED from
                          /root/reference (only when that tree is present: it proves the drop-in
                          claim "existing callers relink unchanged"; the source is not copied)
@@ -171,6 +172,11 @@ def build() -> list:
     built = []
     exe = OUT / "gemm_b200"
     src = ROOT / "samples" / "gemm_b200.cpp"
+    if not exe.exists() or exe.stat().st_mtime < max(p.stat().st_mtime for p in [src, *ROOT.glob("include/**/*.h*")]):
+        _compile(src, exe)
+    built.append(exe)
+    exe = OUT / "gemm_multi_b200"
+    src = ROOT / "samples" / "gemm_multi_b200.cpp"
     if not exe.exists() or exe.stat().st_mtime < max(p.stat().st_mtime for p in [src, *ROOT.glob("include/**/*.h*")]):
         _compile(src, exe)
     built.append(exe)

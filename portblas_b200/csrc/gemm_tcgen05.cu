@@ -40,6 +40,7 @@ PBX_TC_INST_DECL(pbx_tc_inst_f32_pre0);
 PBX_TC_INST_DECL(pbx_tc_inst_f32_pre1);
 PBX_TC_INST_DECL(pbx_tc_inst_f32_pre2);
 PBX_TC_INST_DECL(pbx_tc_inst_f32_pre3);
+PBX_TC_INST_DECL(pbx_tc_inst_f32_pre4);
 PBX_TC_INST_DECL(pbx_tc_inst_f16);
 PBX_TC_INST_DECL(pbx_tc_inst_f16f32);
 PBX_TC_INST_DECL(pbx_tc_inst_bf16);
@@ -99,13 +100,13 @@ bool make_split16_map(CUtensorMap* out, const void* ptr, int64_t mn, int64_t k, 
 
 // Tensor map of C for the TMA-store epilogue: 32 x 32 boxes of the column-major output, no swizzle.
 bool make_c_map(CUtensorMap* out, int es, CUtensorMapDataType dt, void* ptr, int64_t m, int64_t n, int64_t ld,
-                int64_t batch, int64_t stride) {
+                int64_t batch, int64_t stride, int box_m = 32) {
   auto fn = get_encode_fn();
   if (!fn) return false;
   const bool batched = batch > 1;
   cuuint64_t dims[3] = {(cuuint64_t)m, (cuuint64_t)n, (cuuint64_t)(batched ? batch : 1)};
   cuuint64_t strides[2] = {(cuuint64_t)ld * es, (cuuint64_t)(batched ? stride : ld * n) * es};
-  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t box[3] = {(cuuint32_t)box_m, 32, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(out, dt, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -156,10 +157,12 @@ TcPlan make_plan(pbx_handle_t h, const PbxGemmCall& c) {
       }
     }
   }
-  // HBM-bound 16-bit shapes (BASELINE cfg4: 4096 x 256^3, 85 flop/B): measured on B200, 148 independent 128x128
-  // tiles keep DRAM busier than 74 CTA pairs on 256x256 tiles (529 vs 518 TFLOP/s) -- the tensor pipe is a third
-  // loaded either way, what counts is how many independent load streams are in flight.
-  if (!(force && fcg) && !plan.swap && pbx_in_size(c.dtype) == 2) {
+  // HBM-bound 16-bit shapes (BASELINE cfg4: 4096 x 256^3, 85 flop/B).  With the STATIC tile schedule 148 independent
+  // 128x128 tiles kept DRAM busier than 74 CTA pairs on 256x256 tiles (round 1: 529 vs 518 TFLOP/s).  With the dynamic
+  // schedule the pairs win (round 2, same box, burst: 548 vs 490 TFLOP/s = 6.42 vs 5.74 TB/s; cuBLAS 571): a 256x256
+  // tile loads every operand byte exactly once, while the four 128x128 tiles of a batch entry load each panel twice
+  // and lean on L2 to merge the copies (ncu: L2 hit rate 47 %, i.e. half of the load traffic is duplicate).
+  if (!(force && fcg) && !plan.swap && pbx_in_size(c.dtype) == 2 && !h->dynamic_sched) {
     const double flops = 2.0 * (double)c.m * (double)c.n * (double)c.k;
     const double byts = 2.0 * ((double)c.m * c.k + (double)c.k * c.n) + (double)pbx_out_size(c.dtype) * c.m * c.n;
     const Cand small = {1, 128};
@@ -315,7 +318,11 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
     h->last_error = "cuTensorMapEncodeTiled failed";
     return PBX_ERR_CUDA;
   }
-  const int pre_mode = tf32x1 ? 2 : (split16 ? 3 : (pre ? 1 : 0));
+  // no pre-pass: the splitter warps of the kernel make the lo halves -- as bf16 tiles (mode 4: tf32 + 2 x bf16, two
+  // tf32-MMA times per k-step) unless PBX_F32_SPLIT16=0 asks for the 3xTF32 form (mode 0)
+  const char* s16_off = getenv("PBX_F32_SPLIT16");
+  const bool inkernel16 = f32 && !tf32x1 && !pre && !(s16_off != nullptr && s16_off[0] == '0');
+  const int pre_mode = tf32x1 ? 2 : (split16 ? 3 : (pre ? 1 : (inkernel16 ? 4 : 0)));
   h->last_presplit = pre_mode;
   TcParams p;
   p.C = c.C; p.ws = (float*)h->ws;
@@ -344,13 +351,33 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
 
   // 16-bit C with beta == 0 leaves through shared memory + TMA stores when C is TMA-legal
   tm.c = tm.a;  // placeholder when unused (never dereferenced)
+  tm.push.local = tm.a;
+  for (int x = 0; x < 7; ++x) tm.push.peer[x] = tm.a;
   p.tma_store = 0;
+  p.push = 0;
   const bool out16 = (c.dtype == PBX_F16 || c.dtype == PBX_BF16);
   const char* ts_env = getenv("PBX_TMA_STORE");
-  if (out16 && c.beta == 0.0 && slices == 1 && c.n_extra == 0 && !(ts_env && atoi(ts_env) == 0) && ((uintptr_t)c.C % 16 == 0) &&
-      (c.ldc * 2) % 16 == 0 && (c.batch == 1 || (c.sc * 2) % 16 == 0) && c.ldc * 2 < ((int64_t)1 << 40) &&
-      c.sc * 2 < ((int64_t)1 << 40)) {
-    if (make_c_map(&tm.c, 2, dt, c.C, c.m, c.n, c.ldc, c.batch, c.sc)) p.tma_store = 1;
+  auto c_legal = [&](const void* ptr) {
+    return ((uintptr_t)ptr % 16 == 0) && (c.ldc * eo) % 16 == 0 && (c.batch == 1 || (c.sc * eo) % 16 == 0) &&
+           c.ldc * eo < ((int64_t)1 << 40) && c.sc * eo < ((int64_t)1 << 40);
+  };
+  bool peers_legal = true;
+  for (int x = 0; x < c.n_extra; ++x) peers_legal = peers_legal && c_legal(c.c_extra[x]);
+  if (out16 && c.beta == 0.0 && slices == 1 && !(ts_env && atoi(ts_env) == 0) && c_legal(c.C) &&
+      peers_legal) {
+    bool ok = make_c_map(&tm.c, 2, dt, c.C, c.m, c.n, c.ldc, c.batch, c.sc);
+    // multicast GEMM: the staging tiles of the TMA-store epilogue also go to every peer's C
+    for (int x = 0; x < c.n_extra && ok; ++x) ok = make_c_map(&tm.push.peer[x], 2, dt, c.c_extra[x], c.m, c.n, c.ldc, c.batch, c.sc);
+    if (ok) p.tma_store = 1;
+  }
+  // multicast GEMM with 32-bit outputs: asynchronous peer copies by the pusher warp (128 x 32 boxes read back from the
+  // local C); PBX_MULTICAST_PUSH=0 keeps the round-1 form (the epilogue warps store to every copy themselves)
+  const char* push_env = getenv("PBX_MULTICAST_PUSH");
+  if (c.n_extra > 0 && eo == 4 && slices == 1 && !plan.swap && !(push_env && atoi(push_env) == 0) && c_legal(c.C) && peers_legal) {
+    bool ok = make_c_map(&tm.push.local, 4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, c.C, c.m, c.n, c.ldc, c.batch, c.sc, BM);
+    for (int x = 0; x < c.n_extra && ok; ++x)
+      ok = make_c_map(&tm.push.peer[x], 4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, c.c_extra[x], c.m, c.n, c.ldc, c.batch, c.sc, BM);
+    if (ok) p.push = 1;
   }
 
   switch (c.dtype) {
@@ -358,6 +385,7 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
       if (pre_mode == 1) return pbx_tc_inst_f32_pre1(h, cg, bn, a_mn, b_mn, tm, p);
       if (pre_mode == 2) return pbx_tc_inst_f32_pre2(h, cg, bn, a_mn, b_mn, tm, p);
       if (pre_mode == 3) return pbx_tc_inst_f32_pre3(h, cg, bn, a_mn, b_mn, tm, p);
+      if (pre_mode == 4) return pbx_tc_inst_f32_pre4(h, cg, bn, a_mn, b_mn, tm, p);
       return pbx_tc_inst_f32_pre0(h, cg, bn, a_mn, b_mn, tm, p);
     case PBX_F16: return pbx_tc_inst_f16(h, cg, bn, a_mn, b_mn, tm, p);
     case PBX_F16_F32: return pbx_tc_inst_f16f32(h, cg, bn, a_mn, b_mn, tm, p);

@@ -67,10 +67,22 @@ struct TcParams {
   // (the last one re-arms both for the next launch); dynamic == 0 -> static round-robin over the groups
   unsigned int* sched;
   int dynamic;
+  // multicast GEMM, asynchronous form: the peer copies of a finished tile are pushed by TMA (see the pusher warp) instead
+  // of being stored by the epilogue warps
+  int push;
+};
+
+// tensor maps of the multicast GEMM's asynchronous peer copies: the local C (read back, 128 x 32 boxes) and the peers'
+// C (fp32 / fp64-sized outputs: 128 x 32 boxes written by the pusher warp; 16-bit outputs: 32 x 32 boxes written
+// straight from the TMA-store epilogue's staging tiles)
+struct TcPushMaps {
+  CUtensorMap local;
+  CUtensorMap peer[7];
 };
 
 struct TcMaps {
   CUtensorMap a, b, c, alo, blo;
+  TcPushMaps push;
 };
 
 namespace {
@@ -120,6 +132,10 @@ constexpr int ROW_BYTES = 128;  // one swizzle row
 //      (tools/split_emulation.py: <= 2e-7 of sum|a||b|), and bf16 MMAs run at twice the tf32 rate -- two tf32-MMA
 //      times per k-step instead of three.  The bf16 tiles are 32 k wide like the fp32 ones (64-byte rows, 64B swizzle)
 //      and take the place of the lo tiles in the stage: [A raw | B raw | A16 hi | A16 lo | B16 hi | B16 lo]
+//   4  tf32 + 2 x bf16 with the bf16 tiles made IN the kernel: only the raw tiles arrive by TMA, splitter warps convert
+//      every staged tile into the same four bf16 tiles (re-laid out from the 128-byte-swizzled fp32 rows to 64-byte-
+//      swizzled bf16 rows).  For shapes whose arithmetic intensity does not pay for a pre-pass (tall-skinny split-K,
+//      mid-size problems): two tf32-MMA times per k-step instead of PRE == 0's three, and a third less operand traffic
 template <int ES, int BN, int STAGES, int CG, int OS = 4, int PRE = 0>
 struct TcCfg {
   static constexpr bool TF32X3 = (ES == 4);
@@ -137,18 +153,23 @@ struct TcCfg {
   // that it hands to TMA stores, so C leaves the SM as bulk writes instead of 2-byte stores
   static constexpr int EPI_TILE_BYTES = 32 * 32 * OS;
   static constexpr int EPI_BYTES = (OS == 2) ? EPI_WARPS * 2 * EPI_TILE_BYTES : 0;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // + align slack
+  // 32-bit outputs: two 128 x 32 staging boxes of the pusher warp (multicast GEMM): a finished tile is read back from
+  // the local C (L2) and sent to the peers by TMA while the next tile is on the tensor cores
+  static constexpr int PUSH_BOX_BYTES = BM * 32 * OS;
+  static constexpr int PUSH_BYTES = (OS == 4) ? 2 * PUSH_BOX_BYTES : 0;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + PUSH_BYTES + BAR_BYTES + 1024;  // + align slack
   // TMEM: ACC_STAGES accumulators of BN columns (+ for fp32 a BN-column running sum)
   static constexpr int ACC_STAGES = TF32X3 ? ((3 * BN <= 512) ? 2 : 1) : 2;
   static constexpr int RSUM_COL = ACC_STAGES * BN;
   static constexpr int TMEM_COLS = TF32X3 ? 512 : 2 * BN;
-  static constexpr int SPLIT_WARPS = (TF32X3 && PRE == 0) ? 4 : 0;
+  static constexpr int SPLIT_WARPS = (TF32X3 && (PRE == 0 || PRE == 4)) ? 4 : 0;
   static constexpr int TMA_BYTES = RAW_BYTES * ((TF32X3 && (PRE == 1 || PRE == 3)) ? 2 : 1);   // bytes one CTA's producer lands per stage
   static constexpr int NUM_THREADS = 32 * (4 + EPI_WARPS + SPLIT_WARPS);
   static constexpr int NUM_SPLIT_THREADS = 32 * SPLIT_WARPS;
   // tile scheduler ring: the leader's producer lane publishes the next tile index, every other role reads it
   static constexpr int SCHED_SLOTS = 4;
-  static constexpr int SCHED_CONSUMERS = 1 + EPI_WARPS + SPLIT_WARPS;   // MMA lane (leader) / producer lane (peer) + warps
+  // MMA lane (leader) / producer lane (peer) + pusher lane + epilogue and splitter warps
+  static constexpr int SCHED_CONSUMERS = 2 + EPI_WARPS + SPLIT_WARPS;
   static_assert(BN % (32 * 2) == 0 && BN <= 256 && (BN_CTA % 8) == 0, "tile width");
 };
 
@@ -178,7 +199,7 @@ template <typename TIn, typename TOut, int BN, int STAGES, bool A_MN, bool B_MN,
 __global__ void __launch_bounds__(TcCfg<sizeof(TIn), BN, STAGES, CG, sizeof(TOut), PRE>::NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAlo,
-               const __grid_constant__ CUtensorMap tmBlo, const TcParams p) {
+               const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ TcPushMaps tmPush, const TcParams p) {
   using Cfg = TcCfg<sizeof(TIn), BN, STAGES, CG, sizeof(TOut), PRE>;
   static_assert(PRE == 0 || Cfg::TF32X3, "pre-split / single-tf32 modes exist for fp32 only");
   constexpr bool TF32X3 = Cfg::TF32X3;
@@ -189,7 +210,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_base = smem_base + STAGES * Cfg::STAGE_BYTES;
-  const uint32_t bar_base = epi_base + Cfg::EPI_BYTES;
+  const uint32_t push_base = epi_base + Cfg::EPI_BYTES;
+  const uint32_t bar_base = push_base + Cfg::PUSH_BYTES;
   // barrier map (8 B each): full[S] | empty[S] | split[S] | tmem_full[2] | tmem_empty[2] | tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -202,7 +224,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto sfull_bar = [&](int s) { return sched_base + 8u * s; };
   auto sempty_bar = [&](int s) { return sched_base + 8u * (Cfg::SCHED_SLOTS + s); };
   auto stile = [&](int s) { return sched_base + 16u * Cfg::SCHED_SLOTS + 4u * s; };
-  static_assert(8 * (3 * STAGES + 5) + 20 * Cfg::SCHED_SLOTS <= Cfg::BAR_BYTES, "barrier area");
+  // pusher: load barriers of its two staging boxes | count of epilogue warps that finished storing a tile
+  const uint32_t pload_base = sched_base + 20u * Cfg::SCHED_SLOTS;
+  auto pload_bar = [&](int b) { return pload_base + 8u * b; };
+  const uint32_t push_count = pload_base + 16u;
+  static_assert(8 * (3 * STAGES + 5) + 20 * Cfg::SCHED_SLOTS + 24 <= Cfg::BAR_BYTES, "barrier area");
   volatile uint32_t* tmem_ptr_generic = reinterpret_cast<volatile uint32_t*>(
       smem_raw + (tmem_ptr_smem - smem_u32(smem_raw)));
 
@@ -231,6 +257,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(sfull_bar(s), 1);
       mbar_init(sempty_bar(s), CG * Cfg::SCHED_CONSUMERS);
     }
+    mbar_init(pload_bar(0), 1);
+    mbar_init(pload_bar(1), 1);
+    st_shared_u32(push_count, 0u);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -278,7 +307,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       // pair mode without splitters (16-bit, pre-split fp32): both CTAs credit the leader's full barrier (the MMA
       // issuer waits there).  fp32 with in-kernel split: each CTA's splitter warps wait on their OWN full barrier.
-      constexpr bool kLeaderFull = (CG == 2) && (!TF32X3 || PRE != 0);
+      constexpr bool kLeaderFull = (CG == 2) && (!TF32X3 || (PRE != 0 && PRE != 4));
       uint32_t handed = 0;   // hand-overs published (leader) / consumed (peer) so far
       const uint32_t sfull_peer0 = (CG == 2) ? map_to_cta(sfull_bar(0), 1) : 0u;
       const uint32_t stile_peer0 = (CG == 2) ? map_to_cta(stile(0), 1) : 0u;
@@ -428,7 +457,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
           for (int kb = kc0; kb < kc1; ++kb) {
-            constexpr bool kSplit = TF32X3 && PRE == 0;
+            constexpr bool kSplit = TF32X3 && (PRE == 0 || PRE == 4);
             const uint32_t ready = kSplit ? split_bar(stage) : full_bar(stage);
             // fp32 pair mode with in-kernel split: the peer's splitter warps wrote shared memory with ordinary stores
             if (CG == 2 && kSplit) mbar_wait_cluster(ready, phase); else mbar_wait(ready, phase);
@@ -440,7 +469,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint64_t adesc = make_smem_desc(sA + k * A_KSTEP, A_LBO, A_SBO, A_LT);
               const uint64_t bdesc = make_smem_desc(sB + k * B_KSTEP, B_LBO, B_SBO, B_LT);
               const uint32_t acc = (kb > kc0 || k > 0) ? 1u : 0u;
-              if (PRE == 3) {
+              if (PRE == 3 || PRE == 4) {
                 mma(d_tmem, adesc, bdesc, acc);   // hi * hi (tf32 on the raw tiles); the cross terms follow per k-block
               } else if (TF32X3 && PRE != 2) {
                 const uint64_t adesc_lo = make_smem_desc(sA + Cfg::RAW_BYTES + k * A_KSTEP, A_LBO, A_SBO, A_LT);
@@ -452,7 +481,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mma(d_tmem, adesc, bdesc, acc);
               }
             }
-            if (PRE == 3) {
+            if (PRE == 3 || PRE == 4) {
               // cross terms on the bf16 tiles: 64-byte rows (K-major) / 64-byte mn chunks (MN-major), 64B swizzle
               // (layout type 4): SBO = 8 rows x 64 B; MN-major LBO = one 32 x 32 box; UMMA_K = 16
               constexpr uint32_t idesc16 = make_idesc(1u, A_MN, B_MN, BN, Cfg::TILE_M);
@@ -493,6 +522,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tile = (v == 0xFFFFFFFFu) ? p.total_tiles : (int64_t)v;
         }
       }
+    }
+    __syncwarp();
+  } else if (warp == 3) {
+    // ===================== pusher (one lane): asynchronous peer copies of the multicast GEMM =====================
+    // The epilogue warps store a finished tile into the LOCAL C only and count themselves in; this lane then reads the
+    // tile back (L2 hits) in 128 x 32 boxes and sends every box to all peers with bulk tensor stores.  Nothing waits for
+    // NVLink except this lane: the accumulator is released as soon as the local stores are issued, so the transfer of
+    // tile i runs under the mainloop of tile i+1 (round 1 stored to the peers from the epilogue warps: each tile's
+    // 8 x 128 KiB burst had to drain through NVLink before the next MMA could start: 5.28 ms against 4.32 ms at 8 GPUs).
+    if (lane == 0) {
+      uint32_t handed = 0, ntile = 0, chunk = 0;
+      for (int64_t tile = group; tile < p.total_tiles;) {
+        if (Cfg::PUSH_BYTES > 0 && p.push) {
+          const TileCoord tc = decode_tile(p, tile);
+          const int m0 = tc.mt * Cfg::TILE_M + (int)rank * BM;
+          const int n0 = tc.nt * BN;
+          const uint32_t target = (uint32_t)Cfg::EPI_WARPS * (ntile + 1u);
+          while (ld_acquire_shared_u32(push_count) < target) { }
+          for (int j = 0; j < BN / 32; ++j) {
+            if (n0 + 32 * j >= p.N || m0 >= p.M) break;
+            const uint32_t buf = chunk & 1u;
+            bulk_wait_read<1>();   // the stores that last used this box have read it
+            const uint32_t box = push_base + buf * Cfg::PUSH_BOX_BYTES;
+            mbar_expect_tx(pload_bar(buf), Cfg::PUSH_BOX_BYTES);
+            tma_load_3d(box, &tmPush.local, pload_bar(buf), m0, n0 + 32 * j, tc.b);
+            mbar_wait(pload_bar(buf), (chunk >> 1) & 1u);
+            for (int x = 0; x < p.n_extra; ++x) tma_store_3d(&tmPush.peer[x], box, m0, n0 + 32 * j, tc.b);
+            bulk_commit();
+            ++chunk;
+          }
+          ++ntile;
+        }
+        if (!p.dynamic) {
+          tile += num_groups;
+        } else {   // single lane: the consumer protocol without the warp-wide parts
+          const int slot = (int)(handed % Cfg::SCHED_SLOTS);
+          const uint32_t ph = (handed / Cfg::SCHED_SLOTS) & 1u;
+          if (CG == 2) mbar_wait_cluster(sfull_bar(slot), ph); else mbar_wait(sfull_bar(slot), ph);
+          const uint32_t v = ld_shared_u32(stile(slot));
+          uint32_t dep;
+          asm volatile("and.b32 %0, %1, 0;" : "=r"(dep) : "r"(v));
+          if (CG == 2) mbar_arrive_remote(sempty_leader0 + 8u * slot + dep); else mbar_arrive(sempty_bar(slot) + dep);
+          ++handed;
+          tile = (v == 0xFFFFFFFFu) ? p.total_tiles : (int64_t)v;
+        }
+      }
+      if (Cfg::PUSH_BYTES > 0 && p.push) bulk_wait_all();   // every peer copy has left before the CTA retires
     }
     __syncwarp();
   } else if (warp >= 4 && warp < 4 + Cfg::EPI_WARPS) {
@@ -634,6 +710,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) {
               tma_store_3d(&tmC, stage_u32 + buf * Cfg::EPI_TILE_BYTES, (int)m_warp, (int)(n0 + c0), tc.b);
+              // multicast GEMM: the same staging tile goes to every peer's C (bulk stores over NVLink, asynchronous)
+              for (int x = 0; x < p.n_extra; ++x)
+                tma_store_3d(&tmPush.peer[x], stage_u32 + buf * Cfg::EPI_TILE_BYTES, (int)m_warp, (int)(n0 + c0), tc.b);
               bulk_commit();
             }
           } else {
@@ -663,7 +742,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
               // multicast: the same 32 x 32 block goes to every other copy of C (peer memory over NVLink); the stores
               // are posted, so the transfer of this tile overlaps the mainloop of the next one
-              for (int x = 0; x < p.n_extra; ++x) {
+              for (int x = 0; x < (p.push ? 0 : p.n_extra); ++x) {
                 TOut* dx = reinterpret_cast<TOut*>(p.Cx[x]) + c_off;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) OutCvt<TOut>::store(dx + j * p.ldc, __uint_as_float(v[j]));
@@ -675,7 +754,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   float r = p.alpha * __uint_as_float(v[j]);
                   if (!beta0) r += p.beta * OutCvt<TOut>::load(dst + j * p.ldc);
                   OutCvt<TOut>::store(dst + j * p.ldc, r);
-                  for (int x = 0; x < p.n_extra; ++x)
+                  for (int x = 0; x < (p.push ? 0 : p.n_extra); ++x)
                     OutCvt<TOut>::store(reinterpret_cast<TOut*>(p.Cx[x]) + c_off + j * p.ldc, r);
                 }
               }
@@ -689,9 +768,80 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (CG == 2) mbar_arrive_remote(tempty_leader0 + 8u * as); else mbar_arrive(tempty_bar(as));
         }
       }
+      if (Cfg::PUSH_BYTES > 0 && p.push) {
+        // this warp's part of the tile is in the local C: order the stores before the pusher's TMA reads of them
+        // (generic proxy -> async proxy), then count the warp in
+        fence_proxy_async_global();
+        __syncwarp();
+        if (lane == 0) red_release_shared_add(push_count, 1u);
+      }
     }
     if (OUT16 && tma_store && lane == 0) bulk_wait_read<0>();   // staging tiles must outlive their stores
     __syncwarp();
+  } else if (TF32X3 && PRE == 4 && warp >= 4 + Cfg::EPI_WARPS) {
+    // ===================== fp32 -> bf16 (hi, lo) tiles, made in shared memory (each CTA converts what it staged) ========
+    // source: the raw fp32 tile, 128-byte rows in the 128B swizzle (K-major: row = mn index, 16-byte chunk c of the
+    // row sits at c ^ (row % 8)) or, MN-major, 4 KiB boxes of 32 k-rows x 32 mn in the 32B-atom flavour (32-byte unit
+    // u of row r sits at u ^ (r % 4)).  destination: bf16 tiles with 64-byte rows in the 64B swizzle (16-byte chunk c
+    // of row r sits at c ^ ((r / 2) % 4)), the layout the PRE == 3 tensor maps deliver: [A16 hi | A16 lo | B16 hi | B16 lo].
+    const int st = threadIdx.x - 32 * (4 + Cfg::EPI_WARPS);
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t split_leader0 = (CG == 2) ? map_to_cta(split_bar(0), 0) : split_bar(0);
+    auto lo_of = [](float x) {
+      const float d = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+      return d == d ? d : 0.0f;   // inf - inf -> 0
+    };
+    auto cvt8 = [&](const float4 x0, const float4 x1, uint8_t* hi_dst, uint8_t* lo_dst) {
+      __nv_bfloat162 h[4], l[4];
+      h[0] = __floats2bfloat162_rn(x0.x, x0.y); h[1] = __floats2bfloat162_rn(x0.z, x0.w);
+      h[2] = __floats2bfloat162_rn(x1.x, x1.y); h[3] = __floats2bfloat162_rn(x1.z, x1.w);
+      l[0] = __floats2bfloat162_rn(lo_of(x0.x), lo_of(x0.y)); l[1] = __floats2bfloat162_rn(lo_of(x0.z), lo_of(x0.w));
+      l[2] = __floats2bfloat162_rn(lo_of(x1.x), lo_of(x1.y)); l[3] = __floats2bfloat162_rn(lo_of(x1.z), lo_of(x1.w));
+      *reinterpret_cast<uint4*>(hi_dst) = *reinterpret_cast<const uint4*>(h);
+      *reinterpret_cast<uint4*>(lo_dst) = *reinterpret_cast<const uint4*>(l);
+    };
+    // one operand tile of ROWS mn-indices x 32 k
+    auto convert = [&](const uint8_t* raw, uint8_t* hi16, uint8_t* lo16, const int rows, const bool mn_major) {
+      const int items = rows * 4;
+      for (int i = st; i < items; i += Cfg::NUM_SPLIT_THREADS) {
+        const int c = i & 3;
+        if (!mn_major) {
+          const int r = i >> 2;   // mn index; k = 8c .. 8c+7 = fp32 chunks 2c, 2c+1
+          const uint8_t* src = raw + r * 128;
+          const float4 x0 = *reinterpret_cast<const float4*>(src + (((2 * c) ^ (r & 7)) << 4));
+          const float4 x1 = *reinterpret_cast<const float4*>(src + (((2 * c + 1) ^ (r & 7)) << 4));
+          const int off = r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
+          cvt8(x0, x1, hi16 + off, lo16 + off);
+        } else {
+          const int r = (i >> 2) & 31, box = i >> 7;   // k row of the box; mn = 32*box + 8c .. 8c+7 = 32-byte unit c
+          const uint8_t* src = raw + box * 4096 + r * 128 + ((c ^ (r & 3)) << 5);
+          // odd rows read their second half first: the two rows of a quarter-warp then never meet on a bank
+          const int h0 = (r & 1) << 4;
+          const float4 xa = *reinterpret_cast<const float4*>(src + h0);
+          const float4 xb = *reinterpret_cast<const float4*>(src + (h0 ^ 16));
+          const int off = box * 2048 + r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
+          cvt8((r & 1) ? xb : xa, (r & 1) ? xa : xb, hi16 + off, lo16 + off);
+        }
+      }
+    };
+    uint32_t handed = 0;
+    for (int64_t tile = group; tile < p.total_tiles; tile = next_tile(tile, handed)) {
+      const TileCoord tc = decode_tile(p, tile);
+      const int kb0 = tc.slice * p.kb_per_slice;
+      const int kb1 = min(p.kb_total, kb0 + p.kb_per_slice);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        uint8_t* sA = smem_raw + (smem_base - smem_u32(smem_raw)) + stage * Cfg::STAGE_BYTES;
+        uint8_t* sB = sA + Cfg::A_BYTES;
+        uint8_t* s16 = sA + Cfg::RAW_BYTES;
+        convert(sA, s16, s16 + Cfg::A_BYTES / 2, BM, A_MN);
+        convert(sB, s16 + Cfg::A_BYTES, s16 + Cfg::A_BYTES + Cfg::B_BYTES / 2, Cfg::BN_CTA, B_MN);
+        fence_proxy_async();
+        if (CG == 2) mbar_arrive_cluster(split_leader0 + 8u * stage); else mbar_arrive(split_bar(stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
   } else if (TF32X3 && PRE == 0 && warp >= 4 + Cfg::EPI_WARPS) {
     // ===================== fp32 -> (hi, lo) tf32 splitters (each CTA splits what it staged) ==============
     const int st = threadIdx.x - 32 * (4 + Cfg::EPI_WARPS);
@@ -795,7 +945,7 @@ int launch_inst(pbx_handle_t h, const TcMaps& tm, const TcParams& p_in) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = h->pdl ? 2 : 1;
-  PBX_CUDA_CHECK(h, cudaLaunchKernelEx(&cfg, kern, tm.a, tm.b, tm.c, tm.alo, tm.blo, p));
+  PBX_CUDA_CHECK(h, cudaLaunchKernelEx(&cfg, kern, tm.a, tm.b, tm.c, tm.alo, tm.blo, tm.push, p));
   h->launches++;
   return PBX_OK;
 }

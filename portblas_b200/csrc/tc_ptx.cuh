@@ -235,6 +235,21 @@ __device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
+// generic-proxy writes to GLOBAL memory -> visible to later async-proxy (TMA) reads of the same addresses
+__device__ __forceinline__ void fence_proxy_async_global() {
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+__device__ __forceinline__ void red_release_shared_add(uint32_t addr, uint32_t v) {
+  asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_shared_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+// all of this thread's bulk async groups have completed (writes performed, not only their sources read)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---- descriptors -------------------------------------------------------------------------
 // 128-byte-swizzled operand tile.  lbo/sbo in bytes.
 //   K-major : rows of 128 B (one per M/N index), 8-row groups 1024 B apart -> sbo = 1024

@@ -25,16 +25,18 @@ import torch.distributed as dist
 
 def split_range(total: int, world: int, rank: int, align: int = 1) -> Tuple[int, int]:
     """[start, count) of ``rank``'s share of ``total`` units; shares are multiples of ``align``
-    except possibly the last non-empty one; earlier ranks take the remainder."""
+    except possibly the last non-empty one; earlier ranks take the remainder.  A binding of the C-ABI's
+    ``pbx_shard_range`` (portblas_b200/csrc/pbx_multi.cu), so that the one-process-per-GPU path here and the
+    single-process ``pbx_gemm_sharded`` cut every problem identically."""
     if world <= 0 or not (0 <= rank < world):
         raise ValueError("bad world/rank")
-    units = (total + align - 1) // align
-    base, rem = divmod(units, world)
-    u0 = rank * base + min(rank, rem)
-    cnt = base + (1 if rank < rem else 0)
-    start = min(u0 * align, total)
-    end = min((u0 + cnt) * align, total)
-    return start, end - start
+    import ctypes
+    from . import _lib
+    start, count = ctypes.c_int64(0), ctypes.c_int64(0)
+    st = _lib.load().pbx_shard_range(int(total), int(world), int(rank), int(align), ctypes.byref(start), ctypes.byref(count))
+    if st != _lib.OK:
+        raise ValueError("pbx_shard_range: invalid argument")
+    return int(start.value), int(count.value)
 
 
 @dataclasses.dataclass(frozen=True)

@@ -113,7 +113,7 @@ def test_cfg2_dgemm_8192_all_transposes(handle):
 
 def test_cfg3_sgemm_16384(handle):
     _check(handle, torch.float32, "n", "n", 16384, 16384, 16384, 1.0, 0.0)
-    assert handle.last_kernel == "tcgen05" and handle.last_presplit == 1
+    assert handle.last_kernel == "tcgen05" and handle.last_presplit == 3   # tf32 + 2 x bf16 pre-split
     # one M-block shard of the 8-GPU partition (rows [0, 2048) with the ORIGINAL leading dimensions is what a rank runs;
     # here the compact equivalent) and a transposed, beta != 0 variant
     _check(handle, torch.float32, "t", "n", 2048, 16384, 16384, 1.5, 0.5)

@@ -324,14 +324,16 @@ def test_golden_fixtures_gpu(handle):
 
 
 def test_fp32_presplit_operands(handle):
-    """fp32 with the lo halves of A and B pre-split in global memory (PBX_TF32_PRESPLIT=1, the default for
-    compute-bound shapes) must agree with the in-kernel split on every tile configuration, transpose, ragged
+    """fp32 with the tf32 lo halves of A and B pre-split in global memory (PBX_TF32_PRESPLIT=1 with PBX_F32_SPLIT16=0:
+    the 3xTF32 form of the pre-split; the default for compute-bound shapes is the tf32 + 2 x bf16 form, covered by
+    tests/test_split16_gpu.py) must agree with the in-kernel split on every tile configuration, transpose, ragged
     edge, strided batch (incl. stride-0 broadcast), K slice count, the skinny-M operand swap and repacked
-    (odd-ld) operands; and a large square shape must pick it on its own."""
+    (odd-ld) operands; and a large square shape must pick a pre-split mode on its own."""
     pre = ("PBX_TF32_PRESPLIT", "1")
+    no16 = ("PBX_F32_SPLIT16", "0")
     cases = []
     for cfg in ("1,128", "2,128", "2,256"):
-        env = (pre, ("PBX_TC_CONFIG", cfg))
+        env = (pre, no16, ("PBX_TC_CONFIG", cfg))
         for (ta, tb), be in itertools.product(TRANS, [0.0, 0.5]):
             cases.append(Case(dtype="f32", transa=ta, transb=tb, m=392, n=520, k=1096, alpha=1.5, beta=be,
                               kernel=TCGEN05, env=env))
@@ -342,10 +344,10 @@ def test_fp32_presplit_operands(handle):
                           stride_b_mul=2, stride_c_mul=2, kernel=TCGEN05, env=env))
     for (ta, tb) in TRANS:   # skinny-M swap and odd-ld repack under the pre-split
         cases.append(Case(dtype="f32", transa=ta, transb=tb, m=40, n=1000, k=520, alpha=1.5, beta=0.5, kernel=TCGEN05,
-                          env=(pre,)))
+                          env=(pre, no16)))
         cases.append(Case(dtype="f32", transa=ta, transb=tb, m=263, n=131, k=517, alpha=1.5, beta=0.5, offset=1,
-                          kernel=TCGEN05, env=(pre,)))
-    cases.append(Case(dtype="f32", m=512, n=512, k=65536, alpha=1.0, beta=0.0, env=(pre,)))
+                          kernel=TCGEN05, env=(pre, no16)))
+    cases.append(Case(dtype="f32", m=512, n=512, k=65536, alpha=1.0, beta=0.0, env=(pre, no16)))
     _run_all(handle, cases)
     # auto selection on a compute-bound shape, checked on the device against an fp64 product
     import torch
@@ -357,10 +359,12 @@ def test_fp32_presplit_operands(handle):
     c = torch.zeros(n * n, device="cuda")
     blas._gemm(handle, "n", "t", n, n, n, 1.0, a, n, b, n, 0.0, c, n)
     handle.wait()
-    assert handle.last_kernel == "tcgen05" and handle.last_presplit == 1
+    assert handle.last_kernel == "tcgen05" and handle.last_presplit == 3   # tf32 + 2 x bf16
     A, B = a.view(n, n).T.double(), b.view(n, n).T.double()          # column-major -> (rows, cols)
     want = A @ B.T
     bound = A.abs() @ B.abs().T
     assert float(((c.view(n, n).T.double() - want).abs() / bound).max()) <= 1e-5
-    r = run_case(handle, Case(dtype="f32", m=512, n=512, k=65536, alpha=1.0, beta=0.0))   # AI 127: stays in-kernel
-    assert r.ok and handle.last_presplit == 0
+    r = run_case(handle, Case(dtype="f32", m=512, n=512, k=65536, alpha=1.0, beta=0.0))   # AI 127: no pre-pass, the
+    assert r.ok and handle.last_presplit == 4                                             # kernel's splitters make bf16 tiles
+    r = run_case(handle, Case(dtype="f32", m=512, n=512, k=65536, alpha=1.0, beta=0.0, env=(("PBX_F32_SPLIT16", "0"),)))
+    assert r.ok and handle.last_presplit == 0                                             # 3xTF32 in-kernel split on request

@@ -8,7 +8,7 @@ OUT=gpurun_out/$TAG
 mkdir -p $OUT
 for wl in "$@"; do
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:gemm_ -s 3 -c 1 -f -o $OUT/prof_$wl \
-    python bench.py --workload $wl --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/ncu_$wl.log 2>&1
+    python bench.py --workload $wl --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-sub > $OUT/ncu_$wl.log 2>&1
   tail -1 $OUT/ncu_$wl.log
   if [ -f $OUT/prof_$wl.ncu-rep ]; then
     ncu -i $OUT/prof_$wl.ncu-rep --page raw --csv > $OUT/prof_${wl}_raw.csv 2>/dev/null
