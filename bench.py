@@ -93,7 +93,7 @@ def roofline_for(w, avg_ms, traffic, presplit=0):
     """Roof that binds the dominant kernel: tensor pipe for deep contractions, HBM when the arithmetic intensity is
     below the ridge.  fp32 runs as split products on the tf32 / bf16 tensor pipes, so its roof is
     the bf16 figure divided by the tf32-MMA-equivalents one k-step costs: 3xTF32 (presplit 0/1) = 3 tf32 MMAs = 6 bf16
-    times; tf32 + 2 x bf16 (presplit 3) = 1 tf32 + 2 bf16 = 4 bf16 times; single tf32 (presplit 2) = 2."""
+    times; tf32 + 2 x bf16 (presplit 3 / 4) = 1 tf32 + 2 bf16 = 4 bf16 times; single tf32 (presplit 2) = 2."""
     pk = _peaks()
     flops, byts = algorithmic(w)
     ai = flops / byts
@@ -103,9 +103,10 @@ def roofline_for(w, avg_ms, traffic, presplit=0):
         src = ("nominal fp64 40 TF (no fp64 entry in MEASURED_PEAKS.json); measured DMMA pipe ceiling "
                f"{MEASURED_FP64_PIPE_TFLOPS} TF (tools/micro/dmma_rate.cu, profiles/r01/dmma_rate.txt)")
     elif w["dt"] == "f32":
-        div = {2: 2.0, 3: 4.0}.get(presplit, 6.0)
+        div = {2: 2.0, 3: 4.0, 4: 4.0}.get(presplit, 6.0)
         how = {2: "single tf32 product (SB_ENABLE_JOINT_MATRIX=1: reduced-precision fragments): bf16 / 2",
-               3: "tf32 + 2 x bf16 split (1 tf32 MMA + 2 bf16 MMAs per k-step): bf16 / 4"}.get(
+               3: "tf32 + 2 x bf16 split (1 tf32 MMA + 2 bf16 MMAs per k-step; bf16 copies made by a pre-pass): bf16 / 4",
+               4: "tf32 + 2 x bf16 split (1 tf32 MMA + 2 bf16 MMAs per k-step; bf16 tiles made in the kernel): bf16 / 4"}.get(
                    presplit, "3xTF32 (three tf32 MMAs per k-step): bf16 / 6")
         tensor_peak = pk["bf16"] / div
         src = f"fp32 roof for {how}; bf16 {pk['source']}"
@@ -125,7 +126,7 @@ def roofline_for(w, avg_ms, traffic, presplit=0):
         sus = pk["bf16_sustained"] / div
         out["peak_sustained"] = round(sus, 1)
         out["frac_of_sustained"] = round(ach / sus, 4)
-    if w["dt"] == "f32" and presplit == 3:
+    if w["dt"] == "f32" and presplit in (3, 4):
         # the round-1 denominator, for comparison across rounds: three tf32 MMAs per product
         out["frac_of_3xtf32_roof"] = round(ach / (pk["bf16"] / 6.0), 4)
     return out
@@ -512,10 +513,18 @@ class Bench:
         c_h = torch.zeros(c.numel(), dtype=tdt, pin_memory=True)
         torch.cuda.synchronize()
 
+        exchange = self.world > 1 and batch == 1 and bool(w.get("strong")) and w["tb"] == "n" and n % (256 * self.world) == 0
+
         def e2e_step():
-            blas.gemm_host(h, w["ta"], w["tb"], m_loc, n, k, w["alpha"], a_h[a_off:], lda, b_h[b_off:], ldb, w["beta"],
-                           c_h[c_off:], ldc, stridea=m * k if batch > 1 else 0, strideb=k * n if batch > 1 else 0,
-                           stridec=m * n if batch > 1 else 0, batch_size=batch_loc)
+            if exchange:
+                # M-block shards with HOST operands: own rows of A + ONE panel of B over PCIe, the panels exchanged over
+                # NVLink (NCCL all-gather: the path's one real exchange step), own rows of C back
+                self.sharding.gemm_mblock_host(h, w["ta"], w["tb"], m, n, k, w["alpha"], a_h, lda, b_h, ldb, w["beta"], c_h, ldc,
+                                               self.world, self.rank, align=256)
+            else:
+                blas.gemm_host(h, w["ta"], w["tb"], m_loc, n, k, w["alpha"], a_h[a_off:], lda, b_h[b_off:], ldb, w["beta"],
+                               c_h[c_off:], ldc, stridea=m * k if batch > 1 else 0, strideb=k * n if batch > 1 else 0,
+                               stridec=m * n if batch > 1 else 0, batch_size=batch_loc)
         e2e_step()
         e2e_steps = max(1, min(steps, 5))
         self.barrier()
@@ -526,15 +535,18 @@ class Bench:
         mine = (time.perf_counter() - t0) / e2e_steps
         el = self.max_over_ranks(mine)
         c_el = m_loc * n * batch_loc
-        h2d = (m_loc * k * batch_loc + k * n * batch_loc) * es + (c_el * es if w["beta"] != 0 else 0)
+        b_el = k * n * batch_loc // (self.world if exchange else 1)
+        h2d = (m_loc * k * batch_loc + b_el) * es + (c_el * es if w["beta"] != 0 else 0)
         d2h = c_el * es
         del a_h, b_h, c_h
+        api = ("pbx_gemm_host: pinned host buffers, H2D panels | GEMM | D2H panels pipelined on 3 streams "
+               "(= copy_to_device + _gemm + copy_to_host + wait of samples/gemm.cpp)")
+        if exchange:
+            api = ("sharding.gemm_mblock_host: every rank uploads its M-block of A and 1/N of B from pinned host memory, the B "
+                   "panels are exchanged over NVLink (NCCL all-gather), the rank computes its M-block and downloads it")
         return dict(value=round(job_flops / el / 1e12, 3), unit="TFLOP/s", h2d_bytes_per_step=int(h2d),
-                    d2h_bytes_per_step=int(d2h), ms_per_step=round(el * 1e3, 3), steps=e2e_steps,
-                    host_gb_per_s_this_rank=round((h2d + d2h) / mine / 1e9, 1),
-                    api="pbx_gemm_host: pinned host buffers, H2D panels | GEMM | D2H panels pipelined on 3 streams "
-                        "(= copy_to_device + _gemm + copy_to_host + wait of samples/gemm.cpp); at N>1 every rank uploads its "
-                        "M-block of A and all of B and downloads its M-block of C")
+                    d2h_bytes_per_step=int(d2h), bytes_are="per rank", ms_per_step=round(el * 1e3, 3), steps=e2e_steps,
+                    host_gb_per_s_this_rank=round((h2d + d2h) / mine / 1e9, 1), api=api)
 
     def close(self):
         self.h.close()

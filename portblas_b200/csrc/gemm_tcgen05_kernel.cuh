@@ -40,6 +40,7 @@
 #include <stdio.h>
 
 #include <atomic>
+#include <type_traits>
 #include <mutex>
 
 #include <cudaTypedefs.h>
@@ -801,18 +802,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       *reinterpret_cast<uint4*>(hi_dst) = *reinterpret_cast<const uint4*>(h);
       *reinterpret_cast<uint4*>(lo_dst) = *reinterpret_cast<const uint4*>(l);
     };
-    // one operand tile of ROWS mn-indices x 32 k
-    auto convert = [&](const uint8_t* raw, uint8_t* hi16, uint8_t* lo16, const int rows, const bool mn_major) {
-      const int items = rows * 4;
-      for (int i = st; i < items; i += Cfg::NUM_SPLIT_THREADS) {
+    // one operand tile of ROWS mn-indices x 32 k.  A thread owns ROWS*4/128 items of 8 values; all of its loads are
+    // issued before the first conversion (a lone warp per scheduler has nothing else to hide the shared-memory latency)
+    auto convert = [&](const uint8_t* raw, uint8_t* hi16, uint8_t* lo16, auto rows_tag, auto mn_tag) {
+      constexpr int ROWS = decltype(rows_tag)::value;
+      constexpr bool MN = decltype(mn_tag)::value;
+      constexpr int IT = (ROWS * 4 + Cfg::NUM_SPLIT_THREADS - 1) / Cfg::NUM_SPLIT_THREADS;
+      float4 x0[IT], x1[IT];
+      int off[IT];
+#pragma unroll
+      for (int t = 0; t < IT; ++t) {
+        const int i = st + t * Cfg::NUM_SPLIT_THREADS;
         const int c = i & 3;
-        if (!mn_major) {
+        if (ROWS * 4 % Cfg::NUM_SPLIT_THREADS != 0 && i >= ROWS * 4) { off[t] = -1; continue; }
+        if (!MN) {
           const int r = i >> 2;   // mn index; k = 8c .. 8c+7 = fp32 chunks 2c, 2c+1
           const uint8_t* src = raw + r * 128;
-          const float4 x0 = *reinterpret_cast<const float4*>(src + (((2 * c) ^ (r & 7)) << 4));
-          const float4 x1 = *reinterpret_cast<const float4*>(src + (((2 * c + 1) ^ (r & 7)) << 4));
-          const int off = r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
-          cvt8(x0, x1, hi16 + off, lo16 + off);
+          x0[t] = *reinterpret_cast<const float4*>(src + (((2 * c) ^ (r & 7)) << 4));
+          x1[t] = *reinterpret_cast<const float4*>(src + (((2 * c + 1) ^ (r & 7)) << 4));
+          off[t] = r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
         } else {
           const int r = (i >> 2) & 31, box = i >> 7;   // k row of the box; mn = 32*box + 8c .. 8c+7 = 32-byte unit c
           const uint8_t* src = raw + box * 4096 + r * 128 + ((c ^ (r & 3)) << 5);
@@ -820,10 +828,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int h0 = (r & 1) << 4;
           const float4 xa = *reinterpret_cast<const float4*>(src + h0);
           const float4 xb = *reinterpret_cast<const float4*>(src + (h0 ^ 16));
-          const int off = box * 2048 + r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
-          cvt8((r & 1) ? xb : xa, (r & 1) ? xa : xb, hi16 + off, lo16 + off);
+          x0[t] = (r & 1) ? xb : xa;
+          x1[t] = (r & 1) ? xa : xb;
+          off[t] = box * 2048 + r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
         }
       }
+#pragma unroll
+      for (int t = 0; t < IT; ++t)
+        if (ROWS * 4 % Cfg::NUM_SPLIT_THREADS == 0 || off[t] >= 0) cvt8(x0[t], x1[t], hi16 + off[t], lo16 + off[t]);
     };
     uint32_t handed = 0;
     for (int64_t tile = group; tile < p.total_tiles; tile = next_tile(tile, handed)) {
@@ -835,8 +847,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint8_t* sA = smem_raw + (smem_base - smem_u32(smem_raw)) + stage * Cfg::STAGE_BYTES;
         uint8_t* sB = sA + Cfg::A_BYTES;
         uint8_t* s16 = sA + Cfg::RAW_BYTES;
-        convert(sA, s16, s16 + Cfg::A_BYTES / 2, BM, A_MN);
-        convert(sB, s16 + Cfg::A_BYTES, s16 + Cfg::A_BYTES + Cfg::B_BYTES / 2, Cfg::BN_CTA, B_MN);
+        convert(sA, s16, s16 + Cfg::A_BYTES / 2, std::integral_constant<int, BM>{}, std::integral_constant<bool, A_MN>{});
+        convert(sB, s16 + Cfg::A_BYTES, s16 + Cfg::A_BYTES + Cfg::B_BYTES / 2, std::integral_constant<int, Cfg::BN_CTA>{},
+                std::integral_constant<bool, B_MN>{});
         fence_proxy_async();
         if (CG == 2) mbar_arrive_cluster(split_leader0 + 8u * stage); else mbar_arrive(split_bar(stage));
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }

@@ -179,3 +179,49 @@ def gemm_mblock_fused_gather(sb_handle, transa: str, transb: str, m: int, n: int
     ptrs = [c_ptrs[rank] + sh.c_offset * es] + [c_ptrs[r] + sh.c_offset * es for r in range(world) if r != rank]
     blas._gemm_multicast(sb_handle, transa, transb, sh.rows, n, k, alpha, a_local, lda, b, ldb, beta, ptrs, ldc, c_dtype)
     return sh
+
+
+def gemm_mblock_host(sb_handle, transa: str, transb: str, m: int, n: int, k: int, alpha, a_host: torch.Tensor, lda: int,
+                     b_host: torch.Tensor, ldb: int, beta, c_host: torch.Tensor, ldc: int, world: int, rank: int,
+                     group=None, align: int = 256) -> MBlockShard:
+    """``_gemm`` on HOST operands, M-block sharded, one process per GPU -- the torch.distributed twin of the C-ABI's
+    ``pbx_gemm_sharded_host``.  Every rank uploads its rows of op(A) and ONE column panel of op(B) over its own PCIe
+    link; the panels are exchanged over NVLink (the path's one real exchange step: an NCCL all-gather of B), so B
+    crosses PCIe once instead of ``world`` times; then the rank computes its row block and downloads it into its rows
+    of ``c_host``.  Synchronous.  Needs equal panels (n a multiple of align * world) and 'n' for transb; other calls fall
+    back to uploading all of B per rank."""
+    from . import blas
+    sh = shard_mblock(transa, m, lda, world, rank, align)
+    dev = torch.device("cuda", sb_handle.device)
+    ta, tb = transa.lower() != "n", transb.lower() != "n"
+    dt_in, dt_out = a_host.dtype, c_host.dtype
+    rows = sh.rows
+    # ---- this rank's rows of op(A): a strided window of the host matrix -> compact device copy ----
+    if ta:      # A stored k x m: columns [row0, row0 + rows)
+        a_dev = a_host[sh.row0 * lda:].as_strided((rows, k), (lda, 1)).to(dev, non_blocking=True).reshape(-1)
+        lda_d = k
+    else:       # A stored m x k: rows [row0, row0 + rows) of every column
+        a_dev = a_host[sh.row0:].as_strided((k, rows), (lda, 1)).to(dev, non_blocking=True).reshape(-1)
+        lda_d = max(rows, 1)
+    # ---- B: one panel per rank over PCIe, the rest over NVLink ----
+    n0, nn = split_range(n, world, rank, align)
+    equal = (not tb) and nn * world == n and world > 1
+    if equal:
+        panel = b_host[n0 * ldb:].as_strided((nn, k), (ldb, 1)).to(dev, non_blocking=True).reshape(-1)
+        b_dev = torch.empty(n * k, dtype=dt_in, device=dev)
+        dist.all_gather_into_tensor(b_dev, panel, group=group)
+        ldb_d = k
+    else:
+        b_rows, b_cols = (n, k) if tb else (k, n)
+        b_dev = b_host.as_strided((b_cols, b_rows), (ldb, 1)).to(dev, non_blocking=True).reshape(-1)
+        ldb_d = b_rows
+    c_win = c_host[sh.row0:].as_strided((n, rows), (ldc, 1))
+    if float(beta) != 0.0:
+        c_dev = c_win.to(dev, non_blocking=True).reshape(-1)
+    else:
+        c_dev = torch.empty(n * max(rows, 1), dtype=dt_out, device=dev)
+    if rows > 0:
+        blas._gemm(sb_handle, transa, transb, rows, n, k, alpha, a_dev, lda_d, b_dev, ldb_d, beta, c_dev, max(rows, 1))
+        c_win.copy_(c_dev.view(n, rows), non_blocking=True)
+    torch.cuda.current_stream(dev).synchronize()
+    return sh

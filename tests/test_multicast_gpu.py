@@ -72,7 +72,8 @@ def _worker(rank, world, port, q):
         torch.cuda.set_device(rank)
         dev = torch.device("cuda", rank)
         h = SB_Handle(rank)
-        for tdt, (ta, tb), beta in itertools.product([torch.float32, torch.float64], [("n", "n"), ("t", "t")], [0.0, 0.5]):
+        for tdt, (ta, tb), beta in itertools.product([torch.float32, torch.float64, torch.bfloat16], [("n", "n"), ("t", "t")],
+                                                     [0.0, 0.5]):
             m, n, k = 1024 * world, 1536, 2048
             gen = torch.Generator(device=dev).manual_seed(5)       # same seed: every rank generates the same operands
             a = (torch.rand(m * k, device=dev, generator=gen) * 7 - 2).to(tdt)
@@ -92,6 +93,27 @@ def _worker(rank, world, port, q):
             want, bound = _ref(a, b, c0, ta, tb, m, n, k, lda, ldb, m, 1.5, beta)
             rel = float(((c_full.view(n, m).T.double() - want).abs() / bound).max())
             assert rel <= TOL[tdt], f"rank {rank} {tdt} {ta}{tb} beta={beta}: {rel:.2e} kernel={h.last_kernel}"
+            dist.barrier()
+        # HOST operands: every rank uploads its rows of A and one panel of B, the panels are exchanged over NVLink
+        # (an NCCL group beside the test's gloo one), each rank fills its rows of the host C
+        pg = dist.new_group(backend="nccl")   # the B panels travel GPU to GPU
+        for tdt, ta, beta in itertools.product([torch.float32, torch.float64], ["n", "t"], [0.0, 0.5]):
+            m, n, k = 512 * world, 1024, 520
+            gen = torch.Generator().manual_seed(9)
+            a_h = (torch.rand(m * k, generator=gen) * 7 - 2).to(tdt).pin_memory()
+            b_h = (torch.rand(k * n, generator=gen) * 7 - 2).to(tdt).pin_memory()
+            c0_h = (torch.rand(m * n, generator=gen) * 7 - 2).to(tdt)
+            c_h = c0_h.clone().pin_memory()
+            lda = m if ta == "n" else k
+            sh = sharding.gemm_mblock_host(h, ta, "n", m, n, k, 1.5, a_h, lda, b_h, k, beta, c_h, m, world, rank, group=pg)
+            want, bound = _ref(a_h, b_h, c0_h, ta, "n", m, n, k, lda, k, m, 1.5, beta)
+            got = c_h.view(n, m).T.double()
+            rows = slice(sh.row0, sh.row0 + sh.rows)
+            rel = float(((got[rows] - want[rows]).abs() / bound[rows]).max())
+            assert rel <= TOL[tdt], f"rank {rank} host path {tdt} {ta} beta={beta}: {rel:.2e}"
+            other = torch.ones(m, dtype=torch.bool)
+            other[rows] = False
+            assert torch.equal(got[other], c0_h.view(n, m).T.double()[other]), "rows of other ranks were written"
             dist.barrier()
         h.close()
         q.put((rank, "ok"))
