@@ -495,6 +495,9 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const TAcc* __restri
   const int64_t per = m * n;
   const int64_t total = per * batch / VEC;
   struct alignas(sizeof(TAcc) * VEC) Vec { TAcc v[VEC]; };
+  // launched with programmatic stream serialization: the grid is resident while the GEMM that writes the partials
+  // drains; nothing of the workspace is read before that GEMM has completed
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t e = i * VEC;
@@ -724,12 +727,23 @@ int pbx_launch_splitk_reduce(pbx_handle_t h, const PbxGemmCall& c, int slices) {
   return dispatch_dtype(c.dtype, [&](auto* ti, auto* to, auto* ta) -> int {
     using TOut = std::remove_pointer_t<decltype(to)>;
     using TAcc = std::remove_pointer_t<decltype(ta)>;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(256);
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = h->pdl ? 1 : 0;
+    const TAcc* ws = (const TAcc*)h->ws;
+    TOut* C = (TOut*)c.C;
     if (vec4)
-      splitk_reduce_kernel<TOut, TAcc, 4><<<(unsigned)blocks, 256, 0, h->stream>>>(
-          (const TAcc*)h->ws, (TOut*)c.C, c.m, c.n, c.ldc, c.sc, c.batch, slices, c.alpha, c.beta);
+      PBX_CUDA_CHECK(h, cudaLaunchKernelEx(&cfg, splitk_reduce_kernel<TOut, TAcc, 4>, ws, C, c.m, c.n, c.ldc, c.sc, c.batch,
+                                           slices, c.alpha, c.beta));
     else
-      splitk_reduce_kernel<TOut, TAcc, 1><<<(unsigned)blocks, 256, 0, h->stream>>>(
-          (const TAcc*)h->ws, (TOut*)c.C, c.m, c.n, c.ldc, c.sc, c.batch, slices, c.alpha, c.beta);
+      PBX_CUDA_CHECK(h, cudaLaunchKernelEx(&cfg, splitk_reduce_kernel<TOut, TAcc, 1>, ws, C, c.m, c.n, c.ldc, c.sc, c.batch,
+                                           slices, c.alpha, c.beta));
     h->launches++;
     PBX_CUDA_CHECK(h, cudaGetLastError());
     return PBX_OK;

@@ -807,14 +807,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto convert = [&](const uint8_t* raw, uint8_t* hi16, uint8_t* lo16, auto rows_tag, auto mn_tag) {
       constexpr int ROWS = decltype(rows_tag)::value;
       constexpr bool MN = decltype(mn_tag)::value;
-      constexpr int IT = (ROWS * 4 + Cfg::NUM_SPLIT_THREADS - 1) / Cfg::NUM_SPLIT_THREADS;
+      constexpr int NSPLIT = Cfg::NUM_SPLIT_THREADS > 0 ? Cfg::NUM_SPLIT_THREADS : 128;   // (instantiated for every PRE)
+      constexpr int IT = (ROWS * 4 + NSPLIT - 1) / NSPLIT;
       float4 x0[IT], x1[IT];
       int off[IT];
 #pragma unroll
       for (int t = 0; t < IT; ++t) {
-        const int i = st + t * Cfg::NUM_SPLIT_THREADS;
+        const int i = st + t * NSPLIT;
         const int c = i & 3;
-        if (ROWS * 4 % Cfg::NUM_SPLIT_THREADS != 0 && i >= ROWS * 4) { off[t] = -1; continue; }
+        if (ROWS * 4 % NSPLIT != 0 && i >= ROWS * 4) { off[t] = -1; continue; }
         if (!MN) {
           const int r = i >> 2;   // mn index; k = 8c .. 8c+7 = fp32 chunks 2c, 2c+1
           const uint8_t* src = raw + r * 128;
@@ -835,7 +836,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
 #pragma unroll
       for (int t = 0; t < IT; ++t)
-        if (ROWS * 4 % Cfg::NUM_SPLIT_THREADS == 0 || off[t] >= 0) cvt8(x0[t], x1[t], hi16 + off[t], lo16 + off[t]);
+        if (ROWS * 4 % NSPLIT == 0 || off[t] >= 0) cvt8(x0[t], x1[t], hi16 + off[t], lo16 + off[t]);
     };
     uint32_t handed = 0;
     for (int64_t tile = group; tile < p.total_tiles; tile = next_tile(tile, handed)) {

@@ -1,6 +1,8 @@
 #!/bin/bash
 # Round-2 fifth box call (2 GPUs): the pusher warp over real NVLink, the device group on real peers, bench.py at N=2.
 O=gpurun_out/r02e; mkdir -p $O
+set -o pipefail
+python -m portblas_b200.build > /dev/null || { echo "BUILD BROKEN"; exit 9; }
 nvidia-smi --query-gpu=index,name,power.limit --format=csv > $O/gpus.txt; nvidia-smi topo -m >> $O/gpus.txt 2>&1
 timeout 300 python tools/ab_variants.py --workload sgemm_splitk --variants default,split16_off --burst-steps 5 --rounds 3 > $O/ab_splitk.jsonl 2> $O/ab_splitk.err; cat $O/ab_splitk.jsonl
 timeout 300 python tools/ab_variants.py --workload sgemm1024 --variants default,split16_off --burst-steps 200 --rounds 3 > $O/ab_sgemm1024.jsonl 2> $O/ab_1024.err; cat $O/ab_sgemm1024.jsonl
