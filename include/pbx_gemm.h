@@ -271,6 +271,11 @@ int pbx_malloc(pbx_handle_t h, void** dptr, int64_t bytes);
 int pbx_free(pbx_handle_t h, void* dptr);
 int pbx_copy_to_device(pbx_handle_t h, const void* host_src, void* dev_dst, int64_t bytes);
 int pbx_copy_to_host(pbx_handle_t h, const void* dev_src, void* host_dst, int64_t bytes);
+/* rows x cols window of a column-major matrix, each side with its own leading dimension (an M-block of A or C) */
+int pbx_copy2d_to_device(pbx_handle_t h, const void* host_src, int64_t ld_src, void* dev_dst, int64_t ld_dst, int64_t rows,
+                         int64_t cols, int elem_bytes);
+int pbx_copy2d_to_host(pbx_handle_t h, const void* dev_src, int64_t ld_src, void* host_dst, int64_t ld_dst, int64_t rows,
+                       int64_t cols, int elem_bytes);
 int pbx_fill_bytes(pbx_handle_t h, void* dev_dst, int value, int64_t bytes);
 
 int pbx_copy_device_to_device(pbx_handle_t h, const void* dev_src, void* dev_dst, int64_t bytes);

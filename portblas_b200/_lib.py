@@ -81,6 +81,8 @@ SYMBOLS = {
     "pbx_free": (c_int, [c_void_p, c_void_p]),
     "pbx_copy_to_device": (c_int, [c_void_p, c_void_p, c_void_p, c_int64]),
     "pbx_copy_to_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int64]),
+    "pbx_copy2d_to_device": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int]),
+    "pbx_copy2d_to_host": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int]),
     "pbx_fill_bytes": (c_int, [c_void_p, c_void_p, c_int, c_int64]),
     "pbx_copy_device_to_device": (c_int, [c_void_p, c_void_p, c_void_p, c_int64]),
     "pbx_fill": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64]),

@@ -85,6 +85,13 @@ class SB_Handle:
     def wait(self) -> None:
         _check(self, self._lib.pbx_synchronize(self._h))
 
+    @property
+    def stream_ptr(self) -> int:
+        """The cudaStream_t every call of this handle is ordered on.  It is fixed at construction (torch's current stream
+        of the device at that moment) and changed only by ``set_stream`` -- a later ``torch.cuda.stream(...)`` context
+        does not move it (the reference's SB_Handle likewise keeps the one queue it was built with)."""
+        return int(self._lib.pbx_get_stream(self._h) or 0)
+
     def get_num_compute_units(self) -> int:
         return self._lib.pbx_get_num_compute_units(self._h)
 
@@ -254,6 +261,22 @@ def gemm_host(sb_handle: SB_Handle, transa, transb, m, n, k, alpha, a_host: torc
         ctypes.cast(ctypes.pointer(be), ctypes.c_void_p), ctypes.c_void_p(c_host.data_ptr()), int(ldc), int(stridec),
         int(batch_size), int(batch_type))
     _check(sb_handle, st)
+
+
+def copy2d_to_device(sb_handle: SB_Handle, host_src: torch.Tensor, ld_src: int, dev_dst: torch.Tensor, ld_dst: int, rows: int,
+                     cols: int) -> None:
+    """rows x cols window of a column-major host matrix -> device (asynchronous on the handle's stream; pinned memory
+    for a truly asynchronous copy)."""
+    _check(sb_handle, sb_handle._lib.pbx_copy2d_to_device(
+        sb_handle._h, ctypes.c_void_p(host_src.data_ptr()), int(ld_src), ctypes.c_void_p(dev_dst.data_ptr()), int(ld_dst),
+        int(rows), int(cols), int(host_src.element_size())))
+
+
+def copy2d_to_host(sb_handle: SB_Handle, dev_src: torch.Tensor, ld_src: int, host_dst: torch.Tensor, ld_dst: int, rows: int,
+                   cols: int) -> None:
+    _check(sb_handle, sb_handle._lib.pbx_copy2d_to_host(
+        sb_handle._h, ctypes.c_void_p(dev_src.data_ptr()), int(ld_src), ctypes.c_void_p(host_dst.data_ptr()), int(ld_dst),
+        int(rows), int(cols), int(dev_src.element_size())))
 
 
 # ---- multi-GPU: the gather of C fused into the GEMM's stores (include/pbx_gemm.h: pbx_gemm_multicast) --------------

@@ -139,6 +139,44 @@ TcPlan make_plan(pbx_handle_t h, const PbxGemmCall& c) {
     plan.cg = fcg; plan.bn = fbn;
   } else if (want_swap) {
     plan.cg = 1; plan.bn = 64; plan.swap = true;
+  } else if (!(getenv("PBX_PLAN_MODEL") && atoi(getenv("PBX_PLAN_MODEL")) == 0)) {
+    // Cost model (round 2; replaces the ">= 0.6 of a wave" threshold, which left 1.16-wave schedules and rejected
+    // 0.59-wave ones: 384 x 5408 x 3456 ran at 53 TFLOP/s on 86 half-tiles in two rounds).  For every tile
+    // configuration and K-slice count the duration is estimated in units of one K block of a CTA pair on a 256x256 tile:
+    //     rounds(tiles * slices / units) * (K blocks per slice + fill/drain) * cost per K block  +  reduce pass
+    // cost per K block per unit (measured at 8192^3 fp32: 256x256 pairs 328 TFLOP/s, 256x128 pairs 217; a single CTA on
+    // 128x128 reads twice the shared-memory bytes per MAC of a pair): 1.0 / 0.70 / 0.95.
+    const bool f32 = pbx_in_size(c.dtype) == 4;
+    const double t_kb = f32 ? 0.54e-6 : 0.27e-6;     // seconds per K block of a 256x256 pair tile at full clock
+    const double fill = f32 ? 6.0 : 10.0;            // pipeline fill + epilogue drain per tile, in K blocks
+    const double cost_kb[3] = {1.0, 0.70, 0.95};
+    double best = 1e300;
+    for (int ci = 0; ci < 3; ++ci) {
+      const Cand& cd = cands[ci];
+      if (!usable(cd)) continue;
+      const int64_t units = h->sm_count / cd.cg, tiles = tiles_of(cd);
+      int64_t smax = 1;
+      if (c.n_extra == 0 && h->forced_split_k == 0 && kb >= 16) {
+        smax = (2 * units) / tiles;
+        if (smax > kb / 4) smax = kb / 4;
+        if (smax > 64) smax = 64;
+        if (smax < 1) smax = 1;
+      }
+      for (int64_t sl = 1; sl <= smax; ++sl) {
+        const int64_t kbps = (kb + sl - 1) / sl, rounds = (tiles * sl + units - 1) / units;
+        double t = (double)rounds * ((double)kbps + fill) * cost_kb[ci];
+        if (sl > 1)   // partial sums: written once, read once, plus the reduce launch
+          t += (((double)(sl + 1) * 4.0 * (double)c.m * (double)c.n * (double)c.batch) / 5.0e12 + 3.0e-6) / t_kb;
+        if (t < best * 0.97) {   // ties go to the earlier (larger-tile, fewer-slice) choice
+          best = t; plan.cg = cd.cg; plan.bn = cd.bn; plan.slices = (int)sl;
+        }
+      }
+    }
+    if (h->forced_split_k == 0 && c.n_extra == 0) {
+      const int64_t kbps = (kb + plan.slices - 1) / plan.slices;
+      plan.slices = (int)((kb + kbps - 1) / kbps);   // drop empty trailing slices
+      return plan;
+    }
   } else {
     bool found = false;
     for (const Cand& cd : cands) {

@@ -159,6 +159,17 @@ struct TcCfg {
   static constexpr int PUSH_BOX_BYTES = BM * 32 * OS;
   static constexpr int PUSH_BYTES = (OS == 4) ? 2 * PUSH_BOX_BYTES : 0;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + PUSH_BYTES + BAR_BYTES + 1024;  // + align slack
+  // In-kernel split modes (PRE 0 / 4) run TWO rings over the same STAGES * STAGE_BYTES of shared memory: a deep one of
+  // raw tiles (TMA -> splitter -> MMA: its depth has to cover the HBM latency) and a shallow one of derived tiles (the
+  // lo halves / bf16 tiles: splitter -> MMA only, an on-chip hand-over).  With one ring of 3 coupled stages every
+  // in-kernel-split shape ran at one K block per ~1.4 us whatever its size (3 stages in flight over a ~4 us
+  // TMA + split + MMA chain: SGEMM 512 x 512 x 2^20 sat at 1.7 TB/s with the tensor pipe a third busy).
+  static constexpr bool SPLIT_RINGS = TF32X3 && (PRE == 0 || PRE == 4);
+  static constexpr int DER_STAGES = SPLIT_RINGS ? 2 : 0;
+  static constexpr int RAW_STAGES = SPLIT_RINGS ? 2 * STAGES - 2 : STAGES;
+  static constexpr int RAW_STRIDE = SPLIT_RINGS ? RAW_BYTES : STAGE_BYTES;   // bytes between consecutive raw stages
+  static constexpr int DER_BASE = RAW_STAGES * RAW_STRIDE;                   // derived stage d at DER_BASE + d * RAW_BYTES
+  static_assert(!SPLIT_RINGS || DER_BASE + DER_STAGES * RAW_BYTES == STAGES * STAGE_BYTES, "ring split");
   // TMEM: ACC_STAGES accumulators of BN columns (+ for fp32 a BN-column running sum)
   static constexpr int ACC_STAGES = TF32X3 ? ((3 * BN <= 512) ? 2 : 1) : 2;
   static constexpr int RSUM_COL = ACC_STAGES * BN;
@@ -215,13 +226,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t bar_base = push_base + Cfg::PUSH_BYTES;
   // barrier map (8 B each): full[S] | empty[S] | split[S] | tmem_full[2] | tmem_empty[2] | tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto split_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (3 * STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (3 * STAGES + 2 + s); };
-  const uint32_t tmem_ptr_smem = bar_base + 8u * (3 * STAGES + 4);
+  constexpr int RS = Cfg::RAW_STAGES;   // ring of TMA-written stages (== STAGES unless the split rings are in use)
+  constexpr int DS = Cfg::DER_STAGES;   // ring of splitter-written stages
+  auto empty_bar = [&](int s) { return bar_base + 8u * (RS + s); };
+  auto split_bar = [&](int s) { return bar_base + 8u * (2 * RS + s); };   // [DS] with the split rings, else unused
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (3 * RS + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (3 * RS + 2 + s); };
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (3 * RS + 4);
   // scheduler ring: sfull[4] | sempty[4] (the LEADER's are the ones waited on) | tile index [4]
-  const uint32_t sched_base = bar_base + 8u * (3 * STAGES + 5);
+  const uint32_t sched_base = bar_base + 8u * (3 * RS + 5);
   auto sfull_bar = [&](int s) { return sched_base + 8u * s; };
   auto sempty_bar = [&](int s) { return sched_base + 8u * (Cfg::SCHED_SLOTS + s); };
   auto stile = [&](int s) { return sched_base + 16u * Cfg::SCHED_SLOTS + 4u * s; };
@@ -229,7 +242,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t pload_base = sched_base + 20u * Cfg::SCHED_SLOTS;
   auto pload_bar = [&](int b) { return pload_base + 8u * b; };
   const uint32_t push_count = pload_base + 16u;
-  static_assert(8 * (3 * STAGES + 5) + 20 * Cfg::SCHED_SLOTS + 24 <= Cfg::BAR_BYTES, "barrier area");
+  auto dempty_bar = [&](int s) { return pload_base + 24u + 8u * s; };   // derived stage s is free again (MMA -> splitters)
+  static_assert(8 * (3 * RS + 5) + 20 * Cfg::SCHED_SLOTS + 24 + 8 * 2 <= Cfg::BAR_BYTES, "barrier area");
   volatile uint32_t* tmem_ptr_generic = reinterpret_cast<volatile uint32_t*>(
       smem_raw + (tmem_ptr_smem - smem_u32(smem_raw)));
 
@@ -245,10 +259,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (PRE == 1 || PRE == 3) { tma_prefetch_desc(&tmAlo); tma_prefetch_desc(&tmBlo); }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < RS; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
-      mbar_init(split_bar(s), Cfg::NUM_SPLIT_THREADS > 0 ? CG * Cfg::NUM_SPLIT_THREADS : 1);
+    }
+    for (int s = 0; s < DS; ++s) {
+      mbar_init(split_bar(s), CG * Cfg::NUM_SPLIT_THREADS);
+      mbar_init(dempty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -323,7 +340,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int za = p.a_batched ? tc.b : 0, zb = p.b_batched ? tc.b : 0;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sA = smem_base + stage * Cfg::RAW_STRIDE;
           const uint32_t sB = sA + Cfg::A_BYTES;
           const uint32_t fb = full_bar(stage);
           if (kLeaderFull) { if (rank == 0) mbar_expect_tx(fb, 2 * Cfg::TMA_BYTES); }
@@ -383,7 +400,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == RS) { stage = 0; phase ^= 1u; }
         }
         if (!p.dynamic) {
           tile += num_groups;
@@ -442,8 +459,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (CG == 2) tc_mma_2sm<TF32X3>(d, a, b, idesc, acc); else tc_mma<TF32X3>(d, a, b, idesc, acc);
       };
       auto commit = [&](uint32_t bar) { if (CG == 2) tc_commit_2sm(bar); else tc_commit(bar); };
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, dstage = 0;
+      uint32_t phase = 0, dphase = 0;
       int it = 0;  // accumulator hand-offs so far (one per K chunk)
       uint32_t handed = 0;
       for (int64_t tile = group; tile < p.total_tiles;) {
@@ -458,13 +475,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
           for (int kb = kc0; kb < kc1; ++kb) {
-            constexpr bool kSplit = TF32X3 && (PRE == 0 || PRE == 4);
-            const uint32_t ready = kSplit ? split_bar(stage) : full_bar(stage);
-            // fp32 pair mode with in-kernel split: the peer's splitter warps wrote shared memory with ordinary stores
-            if (CG == 2 && kSplit) mbar_wait_cluster(ready, phase); else mbar_wait(ready, phase);
+            constexpr bool kSplit = Cfg::SPLIT_RINGS;
+            // in-kernel split: the derived stage is complete once every splitter thread has arrived (they waited for
+            // the raw stage's TMA first); in pair mode the peer's splitter warps wrote shared memory with ordinary stores
+            if (kSplit) { if (CG == 2) mbar_wait_cluster(split_bar(dstage), dphase); else mbar_wait(split_bar(dstage), dphase); }
+            else mbar_wait(full_bar(stage), phase);
             tc_fence_after();
-            const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
+            const uint32_t sA = smem_base + stage * Cfg::RAW_STRIDE;
             const uint32_t sB = sA + Cfg::A_BYTES;
+            // derived half of the k-block: [A lo | B lo] (3xTF32) or [A16 hi | A16 lo | B16 hi | B16 lo] (bf16 split)
+            const uint32_t sX = kSplit ? smem_base + Cfg::DER_BASE + dstage * Cfg::RAW_BYTES : sA + Cfg::RAW_BYTES;
 #pragma unroll
             for (int k = 0; k < BK / Cfg::UMMA_K; ++k) {
               const uint64_t adesc = make_smem_desc(sA + k * A_KSTEP, A_LBO, A_SBO, A_LT);
@@ -473,8 +493,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (PRE == 3 || PRE == 4) {
                 mma(d_tmem, adesc, bdesc, acc);   // hi * hi (tf32 on the raw tiles); the cross terms follow per k-block
               } else if (TF32X3 && PRE != 2) {
-                const uint64_t adesc_lo = make_smem_desc(sA + Cfg::RAW_BYTES + k * A_KSTEP, A_LBO, A_SBO, A_LT);
-                const uint64_t bdesc_lo = make_smem_desc(sB + Cfg::RAW_BYTES + k * B_KSTEP, B_LBO, B_SBO, B_LT);
+                const uint64_t adesc_lo = make_smem_desc(sX + k * A_KSTEP, A_LBO, A_SBO, A_LT);
+                const uint64_t bdesc_lo = make_smem_desc(sX + Cfg::A_BYTES + k * B_KSTEP, B_LBO, B_SBO, B_LT);
                 mma(d_tmem, adesc_lo, bdesc, acc);
                 mma(d_tmem, adesc, bdesc_lo, 1u);
                 mma(d_tmem, adesc, bdesc, 1u);
@@ -488,7 +508,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               constexpr uint32_t idesc16 = make_idesc(1u, A_MN, B_MN, BN, Cfg::TILE_M);
               constexpr uint32_t A16_KSTEP = A_MN ? 16 * 64 : 32, B16_KSTEP = B_MN ? 16 * 64 : 32;
               constexpr uint32_t A16_LBO = A_MN ? 2048 : 16, B16_LBO = B_MN ? 2048 : 16;
-              const uint32_t sA16 = sA + Cfg::RAW_BYTES, sB16 = sA16 + Cfg::A_BYTES;
+              const uint32_t sA16 = sX, sB16 = sA16 + Cfg::A_BYTES;
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {
                 const uint64_t a_hi = make_smem_desc(sA16 + k * A16_KSTEP, A16_LBO, 512u, 4u);
@@ -505,7 +525,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
             commit(empty_bar(stage));  // smem slot (both CTAs) reusable once these MMAs retire
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            if (kSplit) {
+              commit(dempty_bar(dstage));
+              if (++dstage == DS) { dstage = 0; dphase ^= 1u; }
+            }
+            if (++stage == RS) { stage = 0; phase ^= 1u; }
           }
           commit(tfull_bar(as));  // chunk accumulator complete (both CTAs' epilogues)
         }
@@ -786,8 +810,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // u of row r sits at u ^ (r % 4)).  destination: bf16 tiles with 64-byte rows in the 64B swizzle (16-byte chunk c
     // of row r sits at c ^ ((r / 2) % 4)), the layout the PRE == 3 tensor maps deliver: [A16 hi | A16 lo | B16 hi | B16 lo].
     const int st = threadIdx.x - 32 * (4 + Cfg::EPI_WARPS);
-    int stage = 0;
-    uint32_t phase = 0;
+    int stage = 0, dstage = 0;
+    uint32_t phase = 0, dphase = 0;
     const uint32_t split_leader0 = (CG == 2) ? map_to_cta(split_bar(0), 0) : split_bar(0);
     auto lo_of = [](float x) {
       const float d = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
@@ -844,23 +868,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int kb0 = tc.slice * p.kb_per_slice;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_slice);
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(full_bar(stage), phase);
-        uint8_t* sA = smem_raw + (smem_base - smem_u32(smem_raw)) + stage * Cfg::STAGE_BYTES;
+        mbar_wait(full_bar(stage), phase);            // raw tiles have landed
+        mbar_wait(dempty_bar(dstage), dphase ^ 1u);   // the MMAs that read this derived stage last have retired
+        uint8_t* sm0 = smem_raw + (smem_base - smem_u32(smem_raw));
+        uint8_t* sA = sm0 + stage * Cfg::RAW_STRIDE;
         uint8_t* sB = sA + Cfg::A_BYTES;
-        uint8_t* s16 = sA + Cfg::RAW_BYTES;
+        uint8_t* s16 = sm0 + Cfg::DER_BASE + dstage * Cfg::RAW_BYTES;
         convert(sA, s16, s16 + Cfg::A_BYTES / 2, std::integral_constant<int, BM>{}, std::integral_constant<bool, A_MN>{});
         convert(sB, s16 + Cfg::A_BYTES, s16 + Cfg::A_BYTES + Cfg::B_BYTES / 2, std::integral_constant<int, Cfg::BN_CTA>{},
                 std::integral_constant<bool, B_MN>{});
         fence_proxy_async();
-        if (CG == 2) mbar_arrive_cluster(split_leader0 + 8u * stage); else mbar_arrive(split_bar(stage));
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        if (CG == 2) mbar_arrive_cluster(split_leader0 + 8u * dstage); else mbar_arrive(split_bar(dstage));
+        if (++dstage == DS) { dstage = 0; dphase ^= 1u; }
+        if (++stage == RS) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (TF32X3 && PRE == 0 && warp >= 4 + Cfg::EPI_WARPS) {
     // ===================== fp32 -> (hi, lo) tf32 splitters (each CTA splits what it staged) ==============
     const int st = threadIdx.x - 32 * (4 + Cfg::EPI_WARPS);
-    int stage = 0;
-    uint32_t phase = 0;
+    int stage = 0, dstage = 0;
+    uint32_t phase = 0, dphase = 0;
     constexpr int VEC_PER_STAGE = Cfg::RAW_BYTES / 16;
     const uint32_t split_leader0 = (CG == 2) ? map_to_cta(split_bar(0), 0) : split_bar(0);
     const bool raw_hi = p.raw_hi != 0;
@@ -870,11 +897,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int kb0 = tc.slice * p.kb_per_slice;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_slice);
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(full_bar(stage), phase);
-        // elementwise, so the swizzled placement is preserved: lo tile = raw tile + RAW_BYTES
-        float4* raw = reinterpret_cast<float4*>(smem_raw + (smem_base - smem_u32(smem_raw)) +
-                                                stage * Cfg::STAGE_BYTES);
-        float4* lo = raw + VEC_PER_STAGE;
+        mbar_wait(full_bar(stage), phase);            // raw tiles have landed
+        mbar_wait(dempty_bar(dstage), dphase ^ 1u);   // the MMAs that read this derived stage last have retired
+        // elementwise, so the swizzled placement is preserved: the lo tiles mirror the raw tiles' layout
+        uint8_t* sm0 = smem_raw + (smem_base - smem_u32(smem_raw));
+        float4* raw = reinterpret_cast<float4*>(sm0 + stage * Cfg::RAW_STRIDE);
+        float4* lo = reinterpret_cast<float4*>(sm0 + Cfg::DER_BASE + dstage * Cfg::RAW_BYTES);
         if (raw_hi) {
           // hi operand = the raw fp32 tile (the tensor core reads only the tf32 bits, i.e. truncates);
           // lo = rn_tf32(a - trunc_tf32(a)).  Halves the shared-memory writes of the splitter.
@@ -912,8 +940,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         fence_proxy_async();
-        if (CG == 2) mbar_arrive_cluster(split_leader0 + 8u * stage); else mbar_arrive(split_bar(stage));
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        if (CG == 2) mbar_arrive_cluster(split_leader0 + 8u * dstage); else mbar_arrive(split_bar(dstage));
+        if (++dstage == DS) { dstage = 0; dphase ^= 1u; }
+        if (++stage == RS) { stage = 0; phase ^= 1u; }
       }
     }
   }

@@ -505,6 +505,26 @@ int pbx_copy_to_host(pbx_handle_t h, const void* src, void* dst, int64_t bytes) 
   PBX_CUDA_CHECK(h, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, h->stream));
   return PBX_OK;
 }
+// rows x cols window of a column-major matrix (elem_bytes per element) between host and device, each side with its own
+// leading dimension: the sub-matrix form of copy_to_device / copy_to_host (an M-block of A or C is such a window)
+int pbx_copy2d_to_device(pbx_handle_t h, const void* host_src, int64_t ld_src, void* dev_dst, int64_t ld_dst, int64_t rows,
+                         int64_t cols, int elem_bytes) {
+  if (!h || rows < 0 || cols < 0 || elem_bytes <= 0 || ld_src < rows || ld_dst < rows) return PBX_ERR_INVALID_ARG;
+  if (rows == 0 || cols == 0) return PBX_OK;
+  PBX_DEVICE_GUARD(h);
+  PBX_CUDA_CHECK(h, cudaMemcpy2DAsync(dev_dst, (size_t)ld_dst * elem_bytes, host_src, (size_t)ld_src * elem_bytes,
+                                      (size_t)rows * elem_bytes, (size_t)cols, cudaMemcpyHostToDevice, h->stream));
+  return PBX_OK;
+}
+int pbx_copy2d_to_host(pbx_handle_t h, const void* dev_src, int64_t ld_src, void* host_dst, int64_t ld_dst, int64_t rows,
+                       int64_t cols, int elem_bytes) {
+  if (!h || rows < 0 || cols < 0 || elem_bytes <= 0 || ld_src < rows || ld_dst < rows) return PBX_ERR_INVALID_ARG;
+  if (rows == 0 || cols == 0) return PBX_OK;
+  PBX_DEVICE_GUARD(h);
+  PBX_CUDA_CHECK(h, cudaMemcpy2DAsync(host_dst, (size_t)ld_dst * elem_bytes, dev_src, (size_t)ld_src * elem_bytes,
+                                      (size_t)rows * elem_bytes, (size_t)cols, cudaMemcpyDeviceToHost, h->stream));
+  return PBX_OK;
+}
 int pbx_fill_bytes(pbx_handle_t h, void* dst, int value, int64_t bytes) {
   if (!h || bytes < 0) return PBX_ERR_INVALID_ARG;
   PBX_DEVICE_GUARD(h);

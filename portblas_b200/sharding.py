@@ -196,32 +196,35 @@ def gemm_mblock_host(sb_handle, transa: str, transb: str, m: int, n: int, k: int
     ta, tb = transa.lower() != "n", transb.lower() != "n"
     dt_in, dt_out = a_host.dtype, c_host.dtype
     rows = sh.rows
-    # ---- this rank's rows of op(A): a strided window of the host matrix -> compact device copy ----
-    if ta:      # A stored k x m: columns [row0, row0 + rows)
-        a_dev = a_host[sh.row0 * lda:].as_strided((rows, k), (lda, 1)).to(dev, non_blocking=True).reshape(-1)
-        lda_d = k
-    else:       # A stored m x k: rows [row0, row0 + rows) of every column
-        a_dev = a_host[sh.row0:].as_strided((k, rows), (lda, 1)).to(dev, non_blocking=True).reshape(-1)
-        lda_d = max(rows, 1)
+    # The handle's stream carries the copies and the GEMM; torch's current stream carries the NCCL exchange.
+    hs = torch.cuda.ExternalStream(sb_handle.stream_ptr, device=dev)
+    cur = torch.cuda.current_stream(dev)
+    # ---- this rank's rows of op(A): a window of the host matrix -> compact device copy (2-D DMA, no host-side repack) ----
+    a_rows, a_cols = (k, rows) if ta else (rows, k)
+    a_dev = torch.empty(max(a_rows * a_cols, 1), dtype=dt_in, device=dev)
+    lda_d = max(a_rows, 1)
+    blas.copy2d_to_device(sb_handle, a_host[sh.a_offset:], lda, a_dev, lda_d, a_rows, a_cols)
     # ---- B: one panel per rank over PCIe, the rest over NVLink ----
     n0, nn = split_range(n, world, rank, align)
     equal = (not tb) and nn * world == n and world > 1
     if equal:
-        panel = b_host[n0 * ldb:].as_strided((nn, k), (ldb, 1)).to(dev, non_blocking=True).reshape(-1)
         b_dev = torch.empty(n * k, dtype=dt_in, device=dev)
+        panel = b_dev[n0 * k:(n0 + nn) * k]              # the panel lands in its final place
+        blas.copy2d_to_device(sb_handle, b_host[n0 * ldb:], ldb, panel, k, k, nn)
+        cur.wait_stream(hs)
         dist.all_gather_into_tensor(b_dev, panel, group=group)
+        hs.wait_stream(cur)
         ldb_d = k
     else:
         b_rows, b_cols = (n, k) if tb else (k, n)
-        b_dev = b_host.as_strided((b_cols, b_rows), (ldb, 1)).to(dev, non_blocking=True).reshape(-1)
+        b_dev = torch.empty(b_rows * b_cols, dtype=dt_in, device=dev)
+        blas.copy2d_to_device(sb_handle, b_host, ldb, b_dev, b_rows, b_rows, b_cols)
         ldb_d = b_rows
-    c_win = c_host[sh.row0:].as_strided((n, rows), (ldc, 1))
-    if float(beta) != 0.0:
-        c_dev = c_win.to(dev, non_blocking=True).reshape(-1)
-    else:
-        c_dev = torch.empty(n * max(rows, 1), dtype=dt_out, device=dev)
+    c_dev = torch.empty(n * max(rows, 1), dtype=dt_out, device=dev)
     if rows > 0:
-        blas._gemm(sb_handle, transa, transb, rows, n, k, alpha, a_dev, lda_d, b_dev, ldb_d, beta, c_dev, max(rows, 1))
-        c_win.copy_(c_dev.view(n, rows), non_blocking=True)
-    torch.cuda.current_stream(dev).synchronize()
+        if float(beta) != 0.0:
+            blas.copy2d_to_device(sb_handle, c_host[sh.c_offset:], ldc, c_dev, rows, rows, n)
+        blas._gemm(sb_handle, transa, transb, rows, n, k, alpha, a_dev, lda_d, b_dev, ldb_d, beta, c_dev, rows)
+        blas.copy2d_to_host(sb_handle, c_dev, rows, c_host[sh.c_offset:], ldc, rows, n)
+    sb_handle.wait()
     return sh

@@ -147,6 +147,16 @@ def main():
             torch.cuda.synchronize()
             ts = sorted(evs[i].elapsed_time(evs[i + 1]) / reps for i in range(iters))
             del graph
+            # the same call launched eagerly, back to back (what a caller of blas::_gemm in a loop sees per call: the
+            # larger of the device time and the host-side cost of the call -- tensor-map encodes, selector, ctypes)
+            e_it = iters * (8 if flops <= 5e10 else 1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(e_it):
+                run()
+            e1.record()
+            torch.cuda.synchronize()
+            eager_ms = e0.elapsed_time(e1) / e_it
         else:
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
             evs[0].record()
@@ -163,7 +173,8 @@ def main():
         print(json.dumps(dict(base, kernel=kernel, split_k=split_k, ms=round(ms, 4), tflops=round(tf, 2),
                               gbs=round(byts / ms / 1e6, 1), ai=round(ai, 1),
                               bound="hbm" if ai * HBM_GBS / 1e3 < PEAK_TF[args.dtype] else "tensor",
-                              frac_of_roof=round(tf / roof_tf, 3), timing="graph" if args.graph else "launch", repack=h.last_repack, max_rel_err=float(f"{worst:.3e}"), ok=ok)), flush=True)
+                              frac_of_roof=round(tf / roof_tf, 3), timing="graph" if args.graph else "launch",
+                              eager_ms=round(eager_ms, 4) if args.graph else None, presplit=h.last_presplit, repack=h.last_repack, max_rel_err=float(f"{worst:.3e}"), ok=ok)), flush=True)
         del a, b, c, c0
         if ilv:
             del a_i, b_i, c_i
