@@ -63,10 +63,32 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 // Tensor map of one operand.  kcontig: stored with K contiguous (K-major), else MN contiguous.
-bool make_operand_map(CUtensorMap* out, int es, CUtensorMapDataType dt, const void* ptr, int64_t mn,
+// direct-mapped cache of encoded maps in the handle: `key` holds every argument of the encode call
+bool tmap_cache_get(pbx_handle_t h, const uint64_t (&key)[10], CUtensorMap* out, PbxTmapCacheEntry** slot) {
+  uint64_t hsh = 1469598103934665603ull;
+  for (int i = 0; i < 10; ++i) { hsh ^= key[i]; hsh *= 1099511628211ull; }
+  PbxTmapCacheEntry& e = h->tmap_cache[(hsh >> 20) % 64];
+  *slot = &e;
+  if (!e.valid) return false;
+  for (int i = 0; i < 10; ++i)
+    if (e.key[i] != key[i]) return false;
+  *out = e.map;
+  return true;
+}
+void tmap_cache_put(PbxTmapCacheEntry* slot, const uint64_t (&key)[10], const CUtensorMap& map) {
+  for (int i = 0; i < 10; ++i) slot->key[i] = key[i];
+  slot->map = map;
+  slot->valid = true;
+}
+
+bool make_operand_map(pbx_handle_t h, CUtensorMap* out, int es, CUtensorMapDataType dt, const void* ptr, int64_t mn,
                       int64_t k, int64_t ld, int64_t batch, int64_t stride, bool kcontig, int box_mn) {
   auto fn = get_encode_fn();
   if (!fn) return false;
+  const uint64_t key[10] = {1, (uint64_t)(uintptr_t)ptr, ((uint64_t)es << 32) | (uint64_t)dt, (uint64_t)mn, (uint64_t)k,
+                            (uint64_t)ld, (uint64_t)batch, (uint64_t)stride, (uint64_t)kcontig, (uint64_t)box_mn};
+  PbxTmapCacheEntry* slot = nullptr;
+  if (tmap_cache_get(h, key, out, &slot)) return true;
   const int bk = ROW_BYTES / es;
   const bool batched = batch > 1 && stride > 0;
   cuuint64_t dims[3] = {(cuuint64_t)(kcontig ? k : mn), (cuuint64_t)(kcontig ? mn : k),
@@ -79,15 +101,20 @@ bool make_operand_map(CUtensorMap* out, int es, CUtensorMapDataType dt, const vo
   CUresult r = fn(out, dt, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS) tmap_cache_put(slot, key, *out);
   return r == CUDA_SUCCESS;
 }
 
 // Tensor map of the bf16 copies of one fp32 operand (PRE == 3): the hi copies of all batch entries, then the lo copies,
 // along z (z = which * copies + b; zstride elements apart); 32-element (64-byte) rows, 64B swizzle.
-bool make_split16_map(CUtensorMap* out, const void* ptr, int64_t mn, int64_t k, int64_t ld16, int64_t copies,
+bool make_split16_map(pbx_handle_t h, CUtensorMap* out, const void* ptr, int64_t mn, int64_t k, int64_t ld16, int64_t copies,
                       int64_t zstride, bool kcontig, int box_mn) {
   auto fn = get_encode_fn();
   if (!fn) return false;
+  const uint64_t key[10] = {2, (uint64_t)(uintptr_t)ptr, (uint64_t)mn, (uint64_t)k, (uint64_t)ld16, (uint64_t)copies,
+                            (uint64_t)zstride, (uint64_t)kcontig, (uint64_t)box_mn, 0};
+  PbxTmapCacheEntry* slot = nullptr;
+  if (tmap_cache_get(h, key, out, &slot)) return true;
   cuuint64_t dims[3] = {(cuuint64_t)(kcontig ? k : mn), (cuuint64_t)(kcontig ? mn : k), (cuuint64_t)(2 * copies)};
   cuuint64_t strides[2] = {(cuuint64_t)ld16 * 2, (cuuint64_t)zstride * 2};
   cuuint32_t box[3] = {32, (cuuint32_t)(kcontig ? box_mn : 32), 1};
@@ -95,14 +122,19 @@ bool make_split16_map(CUtensorMap* out, const void* ptr, int64_t mn, int64_t k, 
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS) tmap_cache_put(slot, key, *out);
   return r == CUDA_SUCCESS;
 }
 
 // Tensor map of C for the TMA-store epilogue: 32 x 32 boxes of the column-major output, no swizzle.
-bool make_c_map(CUtensorMap* out, int es, CUtensorMapDataType dt, void* ptr, int64_t m, int64_t n, int64_t ld,
+bool make_c_map(pbx_handle_t h, CUtensorMap* out, int es, CUtensorMapDataType dt, void* ptr, int64_t m, int64_t n, int64_t ld,
                 int64_t batch, int64_t stride, int box_m = 32) {
   auto fn = get_encode_fn();
   if (!fn) return false;
+  const uint64_t key[10] = {3, (uint64_t)(uintptr_t)ptr, ((uint64_t)es << 32) | (uint64_t)dt, (uint64_t)m, (uint64_t)n,
+                            (uint64_t)ld, (uint64_t)batch, (uint64_t)stride, (uint64_t)box_m, 0};
+  PbxTmapCacheEntry* slot = nullptr;
+  if (tmap_cache_get(h, key, out, &slot)) return true;
   const bool batched = batch > 1;
   cuuint64_t dims[3] = {(cuuint64_t)m, (cuuint64_t)n, (cuuint64_t)(batched ? batch : 1)};
   cuuint64_t strides[2] = {(cuuint64_t)ld * es, (cuuint64_t)(batched ? stride : ld * n) * es};
@@ -110,6 +142,7 @@ bool make_c_map(CUtensorMap* out, int es, CUtensorMapDataType dt, void* ptr, int
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(out, dt, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS) tmap_cache_put(slot, key, *out);
   return r == CUDA_SUCCESS;
 }
 
@@ -339,20 +372,20 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
     }
   }
   TcMaps tm;
-  if (!make_operand_map(&tm.a, es, dt, X.p, X.mn, c.k, X.ld, c.batch, X.st, !a_mn, BM) ||
-      !make_operand_map(&tm.b, es, dt, Y.p, Y.mn, c.k, Y.ld, c.batch, Y.st, !b_mn, bn / cg)) {
+  if (!make_operand_map(h, &tm.a, es, dt, X.p, X.mn, c.k, X.ld, c.batch, X.st, !a_mn, BM) ||
+      !make_operand_map(h, &tm.b, es, dt, Y.p, Y.mn, c.k, Y.ld, c.batch, Y.st, !b_mn, bn / cg)) {
     h->last_error = "cuTensorMapEncodeTiled failed";
     return PBX_ERR_CUDA;
   }
   tm.alo = tm.a; tm.blo = tm.b;   // placeholders when unused (never dereferenced)
   if (split16) {
-    if (!make_split16_map(&tm.alo, h->lo[0], X.mn, c.k, s16_ld[0], s16_copies[0], s16_z[0], !a_mn, BM) ||
-        !make_split16_map(&tm.blo, h->lo[1], Y.mn, c.k, s16_ld[1], s16_copies[1], s16_z[1], !b_mn, bn / cg)) {
+    if (!make_split16_map(h, &tm.alo, h->lo[0], X.mn, c.k, s16_ld[0], s16_copies[0], s16_z[0], !a_mn, BM) ||
+        !make_split16_map(h, &tm.blo, h->lo[1], Y.mn, c.k, s16_ld[1], s16_copies[1], s16_z[1], !b_mn, bn / cg)) {
       h->last_error = "cuTensorMapEncodeTiled failed (bf16 split copies)";
       return PBX_ERR_CUDA;
     }
-  } else if (pre && (!make_operand_map(&tm.alo, es, dt, lo_ptr[0], X.mn, c.k, X.ld, c.batch, X.st, !a_mn, BM) ||
-                     !make_operand_map(&tm.blo, es, dt, lo_ptr[1], Y.mn, c.k, Y.ld, c.batch, Y.st, !b_mn, bn / cg))) {
+  } else if (pre && (!make_operand_map(h, &tm.alo, es, dt, lo_ptr[0], X.mn, c.k, X.ld, c.batch, X.st, !a_mn, BM) ||
+                     !make_operand_map(h, &tm.blo, es, dt, lo_ptr[1], Y.mn, c.k, Y.ld, c.batch, Y.st, !b_mn, bn / cg))) {
     h->last_error = "cuTensorMapEncodeTiled failed";
     return PBX_ERR_CUDA;
   }
@@ -403,18 +436,18 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
   for (int x = 0; x < c.n_extra; ++x) peers_legal = peers_legal && c_legal(c.c_extra[x]);
   if (out16 && c.beta == 0.0 && slices == 1 && !(ts_env && atoi(ts_env) == 0) && c_legal(c.C) &&
       peers_legal) {
-    bool ok = make_c_map(&tm.c, 2, dt, c.C, c.m, c.n, c.ldc, c.batch, c.sc);
+    bool ok = make_c_map(h, &tm.c, 2, dt, c.C, c.m, c.n, c.ldc, c.batch, c.sc);
     // multicast GEMM: the staging tiles of the TMA-store epilogue also go to every peer's C
-    for (int x = 0; x < c.n_extra && ok; ++x) ok = make_c_map(&tm.push.peer[x], 2, dt, c.c_extra[x], c.m, c.n, c.ldc, c.batch, c.sc);
+    for (int x = 0; x < c.n_extra && ok; ++x) ok = make_c_map(h, &tm.push.peer[x], 2, dt, c.c_extra[x], c.m, c.n, c.ldc, c.batch, c.sc);
     if (ok) p.tma_store = 1;
   }
   // multicast GEMM with 32-bit outputs: asynchronous peer copies by the pusher warp (128 x 32 boxes read back from the
   // local C); PBX_MULTICAST_PUSH=0 keeps the round-1 form (the epilogue warps store to every copy themselves)
   const char* push_env = getenv("PBX_MULTICAST_PUSH");
   if (c.n_extra > 0 && eo == 4 && slices == 1 && !plan.swap && !(push_env && atoi(push_env) == 0) && c_legal(c.C) && peers_legal) {
-    bool ok = make_c_map(&tm.push.local, 4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, c.C, c.m, c.n, c.ldc, c.batch, c.sc, BM);
+    bool ok = make_c_map(h, &tm.push.local, 4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, c.C, c.m, c.n, c.ldc, c.batch, c.sc, BM);
     for (int x = 0; x < c.n_extra && ok; ++x)
-      ok = make_c_map(&tm.push.peer[x], 4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, c.c_extra[x], c.m, c.n, c.ldc, c.batch, c.sc, BM);
+      ok = make_c_map(h, &tm.push.peer[x], 4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, c.c_extra[x], c.m, c.n, c.ldc, c.batch, c.sc, BM);
     if (ok) p.push = 1;
   }
 

@@ -264,7 +264,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < DS; ++s) {
-      mbar_init(split_bar(s), CG * Cfg::NUM_SPLIT_THREADS);
+      mbar_init(split_bar(s), CG);   // one arrival per CTA: its splitter warps meet on a named barrier first
       mbar_init(dempty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -877,8 +877,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         convert(sA, s16, s16 + Cfg::A_BYTES / 2, std::integral_constant<int, BM>{}, std::integral_constant<bool, A_MN>{});
         convert(sB, s16 + Cfg::A_BYTES, s16 + Cfg::A_BYTES + Cfg::B_BYTES / 2, std::integral_constant<int, Cfg::BN_CTA>{},
                 std::integral_constant<bool, B_MN>{});
+        // every thread makes its tile writes visible to the async proxy, the splitter warps meet on a named barrier and
+        // ONE thread signals the MMA issuer: in pair mode that signal is a remote arrive with a cluster-scope release
+        // (a fence that drains the thread's stores) -- 128 of those per stage and CTA were the bottleneck of the pair
+        // tiles in the in-kernel split modes
         fence_proxy_async();
-        if (CG == 2) mbar_arrive_cluster(split_leader0 + 8u * dstage); else mbar_arrive(split_bar(dstage));
+        named_bar_sync(1, Cfg::NUM_SPLIT_THREADS);
+        if (st == 0) { if (CG == 2) mbar_arrive_cluster(split_leader0 + 8u * dstage); else mbar_arrive(split_bar(dstage)); }
         if (++dstage == DS) { dstage = 0; dphase ^= 1u; }
         if (++stage == RS) { stage = 0; phase ^= 1u; }
       }
@@ -939,8 +944,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             lo[i] = l;
           }
         }
+        // every thread makes its tile writes visible to the async proxy, the splitter warps meet on a named barrier and
+        // ONE thread signals the MMA issuer: in pair mode that signal is a remote arrive with a cluster-scope release
+        // (a fence that drains the thread's stores) -- 128 of those per stage and CTA were the bottleneck of the pair
+        // tiles in the in-kernel split modes
         fence_proxy_async();
-        if (CG == 2) mbar_arrive_cluster(split_leader0 + 8u * dstage); else mbar_arrive(split_bar(dstage));
+        named_bar_sync(1, Cfg::NUM_SPLIT_THREADS);
+        if (st == 0) { if (CG == 2) mbar_arrive_cluster(split_leader0 + 8u * dstage); else mbar_arrive(split_bar(dstage)); }
         if (++dstage == DS) { dstage = 0; dphase ^= 1u; }
         if (++stage == RS) { stage = 0; phase ^= 1u; }
       }

@@ -31,6 +31,14 @@ struct PbxGemmCall {
   void* c_extra[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
+// cuTensorMapEncodeTiled is a pure function of its arguments and costs a microsecond or two per map; a GEMM call
+// needs two to thirteen maps, and callers repeat calls on the same buffers.  The handle keeps the last encodings.
+struct PbxTmapCacheEntry {
+  uint64_t key[10];
+  CUtensorMap map;
+  bool valid = false;
+};
+
 struct pbx_handle_s {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -65,6 +73,7 @@ struct pbx_handle_s {
   unsigned int* tile_sched = nullptr;
   int dynamic_sched = 1;
   int pdl = 1;
+  PbxTmapCacheEntry tmap_cache[64];
   // staging buffers for pbx_gemm_host
   void* stage[3] = {nullptr, nullptr, nullptr};
   int64_t stage_bytes[3] = {0, 0, 0};

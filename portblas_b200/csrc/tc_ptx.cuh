@@ -250,6 +250,11 @@ __device__ __forceinline__ uint32_t ld_acquire_shared_u32(uint32_t addr) {
 // all of this thread's bulk async groups have completed (writes performed, not only their sources read)
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// barrier `id` (1..15; 0 is __syncthreads) over `nthreads` threads (a multiple of 32) of the CTA
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---- descriptors -------------------------------------------------------------------------
 // 128-byte-swizzled operand tile.  lbo/sbo in bytes.
 //   K-major : rows of 128 B (one per M/N index), 8-row groups 1024 B apart -> sbo = 1024
