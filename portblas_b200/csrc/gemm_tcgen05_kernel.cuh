@@ -877,13 +877,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         convert(sA, s16, s16 + Cfg::A_BYTES / 2, std::integral_constant<int, BM>{}, std::integral_constant<bool, A_MN>{});
         convert(sB, s16 + Cfg::A_BYTES, s16 + Cfg::A_BYTES + Cfg::B_BYTES / 2, std::integral_constant<int, Cfg::BN_CTA>{},
                 std::integral_constant<bool, B_MN>{});
-        // every thread makes its tile writes visible to the async proxy, the splitter warps meet on a named barrier and
-        // ONE thread signals the MMA issuer: in pair mode that signal is a remote arrive with a cluster-scope release
-        // (a fence that drains the thread's stores) -- 128 of those per stage and CTA were the bottleneck of the pair
-        // tiles in the in-kernel split modes
+        // every thread makes its tile writes visible to the async proxy (the tensor core reads them through it), the
+        // splitter warps meet on a named barrier and ONE thread signals the MMA issuer.  In pair mode that signal is a
+        // remote arrive; it carries no fence of its own -- a cluster-scope release compiles to MEMBAR.ALL.GPU, and 128
+        // of those per stage and CTA (round 1) held the pair tiles of the in-kernel split modes at 1.6 us per K block
+        // against 0.54 us of MMA time (ncu: the MMA lane waiting on this barrier, the splitters on the MMA's commit)
         fence_proxy_async();
         named_bar_sync(1, Cfg::NUM_SPLIT_THREADS);
-        if (st == 0) { if (CG == 2) mbar_arrive_cluster(split_leader0 + 8u * dstage); else mbar_arrive(split_bar(dstage)); }
+        if (st == 0) { if (CG == 2) mbar_arrive_relaxed_cluster(split_leader0 + 8u * dstage); else mbar_arrive(split_bar(dstage)); }
         if (++dstage == DS) { dstage = 0; dphase ^= 1u; }
         if (++stage == RS) { stage = 0; phase ^= 1u; }
       }
@@ -944,13 +945,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             lo[i] = l;
           }
         }
-        // every thread makes its tile writes visible to the async proxy, the splitter warps meet on a named barrier and
-        // ONE thread signals the MMA issuer: in pair mode that signal is a remote arrive with a cluster-scope release
-        // (a fence that drains the thread's stores) -- 128 of those per stage and CTA were the bottleneck of the pair
-        // tiles in the in-kernel split modes
+        // every thread makes its tile writes visible to the async proxy (the tensor core reads them through it), the
+        // splitter warps meet on a named barrier and ONE thread signals the MMA issuer.  In pair mode that signal is a
+        // remote arrive; it carries no fence of its own -- a cluster-scope release compiles to MEMBAR.ALL.GPU, and 128
+        // of those per stage and CTA (round 1) held the pair tiles of the in-kernel split modes at 1.6 us per K block
+        // against 0.54 us of MMA time (ncu: the MMA lane waiting on this barrier, the splitters on the MMA's commit)
         fence_proxy_async();
         named_bar_sync(1, Cfg::NUM_SPLIT_THREADS);
-        if (st == 0) { if (CG == 2) mbar_arrive_cluster(split_leader0 + 8u * dstage); else mbar_arrive(split_bar(dstage)); }
+        if (st == 0) { if (CG == 2) mbar_arrive_relaxed_cluster(split_leader0 + 8u * dstage); else mbar_arrive(split_bar(dstage)); }
         if (++dstage == DS) { dstage = 0; dphase ^= 1u; }
         if (++stage == RS) { stage = 0; phase ^= 1u; }
       }
