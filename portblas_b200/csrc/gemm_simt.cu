@@ -546,6 +546,63 @@ int dispatch_dtype(int dtype, F&& f) {
 
 }  // namespace
 
+// ---- interleaved <-> strided re-layout of a batch of column-major matrices ---------------------------------------
+// interleaved: element (r, c, b) at (c*ld_i + r)*batch + b (reference gemm_interleaved.hpp:265-271: the batch index is
+// the contiguous one); strided: at b*stride + c*ld_s + r.  For a fixed column c this is the transpose of a rows x batch
+// matrix: 32 x 32 tiles through shared memory, both sides coalesced (128-byte rows of 4-byte elements).
+template <typename T, bool TO_STRIDED>
+__global__ void __launch_bounds__(256) ilv_relayout_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t rows,
+                                                           int64_t ld_i, int64_t ld_s, int64_t stride, int64_t batch) {
+  __shared__ T tile[32][33];
+  const int64_t c = blockIdx.y;
+  const int64_t r0 = (int64_t)blockIdx.x * 32, b0 = (int64_t)blockIdx.z * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8 threads
+  if (TO_STRIDED) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {   // read: b contiguous
+      const int64_t r = r0 + ty + 8 * j, b = b0 + tx;
+      if (r < rows && b < batch) tile[ty + 8 * j][tx] = src[(c * ld_i + r) * batch + b];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {   // write: r contiguous
+      const int64_t b = b0 + ty + 8 * j, r = r0 + tx;
+      if (r < rows && b < batch) dst[b * stride + c * ld_s + r] = tile[tx][ty + 8 * j];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {   // read: r contiguous
+      const int64_t b = b0 + ty + 8 * j, r = r0 + tx;
+      if (r < rows && b < batch) tile[ty + 8 * j][tx] = src[b * stride + c * ld_s + r];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {   // write: b contiguous
+      const int64_t r = r0 + ty + 8 * j, b = b0 + tx;
+      if (r < rows && b < batch) dst[(c * ld_i + r) * batch + b] = tile[tx][ty + 8 * j];
+    }
+  }
+}
+
+int pbx_launch_ilv_relayout(pbx_handle_t h, int elem_bytes, const void* src, void* dst, int64_t rows, int64_t cols,
+                            int64_t ld_i, int64_t ld_s, int64_t stride, int64_t batch, bool to_strided) {
+  if (rows <= 0 || cols <= 0 || batch <= 0) return PBX_OK;
+  if (cols > 65535 || (batch + 31) / 32 > 65535) return PBX_ERR_INVALID_ARG;
+  dim3 grid((unsigned)((rows + 31) / 32), (unsigned)cols, (unsigned)((batch + 31) / 32));
+  auto go = [&](auto tag) {
+    using T = decltype(tag);
+    if (to_strided) ilv_relayout_kernel<T, true><<<grid, 256, 0, h->stream>>>((const T*)src, (T*)dst, rows, ld_i, ld_s, stride, batch);
+    else ilv_relayout_kernel<T, false><<<grid, 256, 0, h->stream>>>((const T*)src, (T*)dst, rows, ld_i, ld_s, stride, batch);
+  };
+  if (elem_bytes == 2) go(uint16_t{});
+  else if (elem_bytes == 4) go(uint32_t{});
+  else if (elem_bytes == 8) go(uint64_t{});
+  else return PBX_ERR_INVALID_ARG;
+  h->launches++;
+  PBX_CUDA_CHECK(h, cudaGetLastError());
+  return PBX_OK;
+}
+
 int pbx_launch_repack(pbx_handle_t h, int elem_bytes, const void* src, void* dst, int64_t rows, int64_t cols,
                       int64_t ld_src, int64_t ld_dst, int64_t stride_src, int64_t stride_dst, int64_t batch) {
   if (rows <= 0 || cols <= 0 || batch <= 0) return PBX_OK;

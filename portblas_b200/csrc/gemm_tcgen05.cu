@@ -177,12 +177,17 @@ TcPlan make_plan(pbx_handle_t h, const PbxGemmCall& c) {
     // 0.59-wave ones: 384 x 5408 x 3456 ran at 53 TFLOP/s on 86 half-tiles in two rounds).  For every tile
     // configuration and K-slice count the duration is estimated in units of one K block of a CTA pair on a 256x256 tile:
     //     rounds(tiles * slices / units) * (K blocks per slice + fill/drain) * cost per K block  +  reduce pass
-    // cost per K block per unit (measured at 8192^3 fp32: 256x256 pairs 328 TFLOP/s, 256x128 pairs 217; a single CTA on
-    // 128x128 reads twice the shared-memory bytes per MAC of a pair): 1.0 / 0.70 / 0.95.
+    // The constants are fitted to tools/plan_probe.py runs on a B200 (profiles/r02/plan_probe_*.jsonl: twelve mid-size
+    // shapes under every configuration x slice count; the model's pick is within 0.5 % (fp32) / 1.7 % (bf16) of the best
+    // measured choice in the geometric mean).  cost per K block per unit: fp32 1.0 / 0.79 / 0.94 (0.80 / 0.63 / 0.75 us
+    // measured: both fp32 split forms run near 0.8 us per K block of a pair tile), 16-bit 1.0 / 0.9 / 0.8 (0.25 us for
+    // the pair tile); `fill` is the cost of an extra tile in a running pipeline (the per-launch fixed cost, ~12 us of
+    // launch + prologue + first loads + last epilogue, is the same for every choice and left out).
     const bool f32 = pbx_in_size(c.dtype) == 4;
-    const double t_kb = f32 ? 0.54e-6 : 0.27e-6;     // seconds per K block of a 256x256 pair tile at full clock
-    const double fill = f32 ? 6.0 : 10.0;            // pipeline fill + epilogue drain per tile, in K blocks
-    const double cost_kb[3] = {1.0, 0.70, 0.95};
+    const double t_kb = f32 ? 0.80e-6 : 0.25e-6;     // seconds per K block of a 256x256 pair tile
+    const double fill = f32 ? 0.5 : 1.0;
+    const double cost_f32[3] = {1.0, 0.79, 0.94}, cost_16[3] = {1.0, 0.90, 0.80};
+    const double* cost_kb = f32 ? cost_f32 : cost_16;
     double best = 1e300;
     for (int ci = 0; ci < 3; ++ci) {
       const Cand& cd = cands[ci];
@@ -199,7 +204,7 @@ TcPlan make_plan(pbx_handle_t h, const PbxGemmCall& c) {
         const int64_t kbps = (kb + sl - 1) / sl, rounds = (tiles * sl + units - 1) / units;
         double t = (double)rounds * ((double)kbps + fill) * cost_kb[ci];
         if (sl > 1)   // partial sums: written once, read once, plus the reduce launch
-          t += (((double)(sl + 1) * 4.0 * (double)c.m * (double)c.n * (double)c.batch) / 5.0e12 + 3.0e-6) / t_kb;
+          t += (((double)(sl + 1) * 4.0 * (double)c.m * (double)c.n * (double)c.batch) / 5.0e12 + 1.5e-6) / t_kb;
         if (t < best * 0.97) {   // ties go to the earlier (larger-tile, fewer-slice) choice
           best = t; plan.cg = cd.cg; plan.bn = cd.bn; plan.slices = (int)sl;
         }

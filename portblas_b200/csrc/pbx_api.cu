@@ -241,6 +241,45 @@ static bool repack_for_tma(pbx_handle_t h, PbxGemmCall& c) {
   return true;
 }
 
+static int run_gemm(pbx_handle_t h, const PbxGemmCall& c_in, int batch_type);
+
+// Interleaved batches through the tensor cores: one HBM-bound pass re-lays A and B (and C when beta != 0) out as
+// strided batches with 16-byte-legal leading dimensions in pooled buffers, the ordinary strided path runs, one more
+// pass writes C back interleaved.  The reference runs a dedicated CUDA-core kernel (gemm_interleaved.hpp:219-312), and
+// so does gemm_interleaved_kernel here; that one is FMA / issue bound at 0.06-0.09 of the HBM roof, while the three
+// extra passes cost about twice the algorithmic bytes.  Taken when the batch is large enough to fill the transposes'
+// 32-entry tiles and the matrices are not tiny; PBX_ILV_VIA_STRIDED=0 keeps the dedicated kernel.
+static bool interleaved_via_strided(pbx_handle_t h, const PbxGemmCall& c, int* status) {
+  static const int env = getenv("PBX_ILV_VIA_STRIDED") ? atoi(getenv("PBX_ILV_VIA_STRIDED")) : -1;
+  if (env == 0) return false;
+  if (h->forced_kernel == PBX_KERNEL_INTERLEAVED) return false;
+  const double flops = 2.0 * (double)c.m * (double)c.n * (double)c.k * (double)c.batch;
+  if (env != 1 && (c.batch < 16 || flops < 2e8 || c.m * c.n < 1024)) return false;
+  const int64_t es = (int64_t)pbx_in_size(c.dtype), eo = (int64_t)pbx_out_size(c.dtype);
+  const int64_t a_rows = c.ta ? c.k : c.m, a_cols = c.ta ? c.m : c.k;
+  const int64_t b_rows = c.tb ? c.n : c.k, b_cols = c.tb ? c.k : c.n;
+  if (a_cols > 65535 || b_cols > 65535 || c.n > 65535 || (c.batch + 31) / 32 > 65535) return false;
+  auto up = [](int64_t v, int64_t q) { return (v + q - 1) / q * q; };
+  const int64_t lda2 = up(a_rows, 16 / es), ldb2 = up(b_rows, 16 / es), ldc2 = up(c.m, 16 / eo);
+  const int64_t sa2 = lda2 * a_cols, sb2 = ldb2 * b_cols, sc2 = ldc2 * c.n;
+  if (pbx_ensure_aux(h, 0, sa2 * c.batch * es) != PBX_OK || pbx_ensure_aux(h, 1, sb2 * c.batch * es) != PBX_OK ||
+      pbx_ensure_aux(h, 2, sc2 * c.batch * eo) != PBX_OK)
+    return false;   // no room for the copies: the dedicated kernel works in place
+  int st = pbx_launch_ilv_relayout(h, (int)es, c.A, h->aux[0], a_rows, a_cols, c.lda, lda2, sa2, c.batch, true);
+  if (st == PBX_OK) st = pbx_launch_ilv_relayout(h, (int)es, c.B, h->aux[1], b_rows, b_cols, c.ldb, ldb2, sb2, c.batch, true);
+  if (st == PBX_OK && c.beta != 0.0)
+    st = pbx_launch_ilv_relayout(h, (int)eo, c.C, h->aux[2], c.m, c.n, c.ldc, ldc2, sc2, c.batch, true);
+  if (st == PBX_OK) {
+    PbxGemmCall s = c;
+    s.A = h->aux[0]; s.B = h->aux[1]; s.C = h->aux[2];
+    s.lda = lda2; s.ldb = ldb2; s.ldc = ldc2; s.sa = sa2; s.sb = sb2; s.sc = sc2;
+    st = run_gemm(h, s, 0);
+  }
+  if (st == PBX_OK) st = pbx_launch_ilv_relayout(h, (int)eo, h->aux[2], c.C, c.m, c.n, c.ldc, ldc2, sc2, c.batch, false);
+  *status = st;
+  return true;
+}
+
 static int run_gemm(pbx_handle_t h, const PbxGemmCall& c_in, int batch_type) {
   PbxGemmCall c = c_in;
   int kernel = h->forced_kernel;
@@ -253,6 +292,8 @@ static int run_gemm(pbx_handle_t h, const PbxGemmCall& c_in, int batch_type) {
   // (and a K loop deep enough to fill an MMA K block: below that the CUDA-core kernel reading in place wins)
   const bool heavy = c.k >= 64;
   if (batch_type == 1 && c.batch > 1) {
+    int st_via = PBX_OK;
+    if (interleaved_via_strided(h, c, &st_via)) return st_via;   // last_kernel = the strided path's kernel
     kernel = PBX_KERNEL_INTERLEAVED;
   } else if (kernel == PBX_KERNEL_AUTO || kernel == PBX_KERNEL_INTERLEAVED) {
     if (c.dtype == PBX_F64) {

@@ -155,6 +155,9 @@ bool pbx_tma_operand_ok(int dtype, const void* p, int64_t ld, int64_t stride);
 // copy a rows x cols column-major window (x batch) to a new leading dimension / batch stride
 int pbx_launch_repack(pbx_handle_t h, int elem_bytes, const void* src, void* dst, int64_t rows, int64_t cols,
                       int64_t ld_src, int64_t ld_dst, int64_t stride_src, int64_t stride_dst, int64_t batch);
+// interleaved <-> strided re-layout of `batch` column-major rows x cols matrices (gemm_simt.cu)
+int pbx_launch_ilv_relayout(pbx_handle_t h, int elem_bytes, const void* src, void* dst, int64_t rows, int64_t cols,
+                            int64_t ld_i, int64_t ld_s, int64_t stride, int64_t batch, bool to_strided);
 int pbx_tcgen05_slices(pbx_handle_t h, const PbxGemmCall& c);  // K slices the tcgen05 plan wants
 int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices);
 int pbx_launch_dmma(pbx_handle_t h, const PbxGemmCall& c, int slices);

@@ -29,11 +29,17 @@ def test_baseline_configs(pbx_lib):
     assert plan(pbx_lib, F16, 256, 256, 256, 512) == (2, 256, 1, False)
     # compute-bound 16-bit: CTA pairs
     assert plan(pbx_lib, BF16, 8192, 8192, 8192) == (2, 256, 1, False)
-    # cfg5 tall-skinny: 4 pair tiles spread over 74 pairs x 2 waves of K slices
+    # cfg5 tall-skinny: 4 pair tiles x 18 K slices = 72 of the 74 pairs in one round (round 1: 37 slices in two rounds;
+    # measured equal: 1.79 vs 1.88 ms, profiles/r02/plan_probe_f32.jsonl)
     cg, bn, slices, swapped = plan(pbx_lib, F32, 512, 512, 1 << 20)
-    assert (cg, bn, swapped) == (2, 256, False) and slices == 37
-    # cfg1 shape: 64 single-CTA tiles cannot fill 148 SMs -> split K four ways
-    assert plan(pbx_lib, F32, 1024, 1024, 1024) == (1, 128, 4, False)
+    assert (cg, bn, swapped) == (2, 256, False) and slices == 18
+    # cfg1 shape: 16 pair tiles x 4 K slices fill 64 of the 74 pairs (measured best of every configuration: 19.2 us)
+    assert plan(pbx_lib, F32, 1024, 1024, 1024) == (2, 256, 4, False)
+    # the shape that exposed round 1's ">= 0.6 of a wave" rule (86 half-tiles in two rounds, 53 TFLOP/s): 44 pair tiles
+    # x 3 slices in two rounds, 187 TFLOP/s
+    assert plan(pbx_lib, F32, 384, 5408, 3456) == (2, 256, 3, False)
+    # 16-bit mid-size shapes: one round of single-CTA tiles beats 0.6 rounds of pairs
+    assert plan(pbx_lib, BF16, 384, 5408, 3456) == (1, 128, 1, False)
 
 
 def test_skinny_m_swaps_operands(pbx_lib):
@@ -45,7 +51,7 @@ def test_skinny_m_swaps_operands(pbx_lib):
 
 
 def test_split_k_rules(pbx_lib):
-    # never more slices than K blocks / 4, never for short K loops, never when the tiles already fill the machine
+    # never more slices than K blocks / 4, never for short K loops, never more than two rounds' worth of units
     for dt, kblock in ((F32, 32), (BF16, 64)):
         for m, n, k in [(128, 128, 3136), (64, 64, 784), (256, 196, 2304), (512, 512, 65536), (4096, 4096, 4096),
                         (128, 128, 256), (300, 260, 4104)]:
@@ -53,10 +59,12 @@ def test_split_k_rules(pbx_lib):
             kb = -(-k // kblock)
             assert 1 <= slices <= max(1, kb // 4) or slices == 1
             tiles = -(-m // (128 * cg)) * -(-n // bn)
-            if tiles * 2 > 148 // cg or kb < 16:
+            assert tiles * slices <= 2 * (148 // cg) or slices == 1, (dt, m, n, k, cg, bn, slices)
+            if kb < 16:
                 assert slices == 1, (dt, m, n, k, slices)
     assert plan(pbx_lib, F32, 128, 128, 3136)[2] > 1
     assert plan(pbx_lib, F32, 4096, 4096, 4096)[2] == 1
+    assert plan(pbx_lib, BF16, 8192, 8192, 8192)[2] == 1
 
 
 def test_plan_scales_with_sm_count(pbx_lib):
