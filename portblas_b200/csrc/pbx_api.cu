@@ -250,7 +250,7 @@ static int run_gemm(pbx_handle_t h, const PbxGemmCall& c_in, int batch_type);
 // extra passes cost about twice the algorithmic bytes.  Taken when the batch is large enough to fill the transposes'
 // 32-entry tiles and the matrices are not tiny; PBX_ILV_VIA_STRIDED=0 keeps the dedicated kernel.
 static bool interleaved_via_strided(pbx_handle_t h, const PbxGemmCall& c, int* status) {
-  static const int env = getenv("PBX_ILV_VIA_STRIDED") ? atoi(getenv("PBX_ILV_VIA_STRIDED")) : -1;
+  const int env = getenv("PBX_ILV_VIA_STRIDED") ? atoi(getenv("PBX_ILV_VIA_STRIDED")) : -1;   // 0 never, 1 always (testing)
   if (env == 0) return false;
   if (h->forced_kernel == PBX_KERNEL_INTERLEAVED) return false;
   const double flops = 2.0 * (double)c.m * (double)c.n * (double)c.k * (double)c.batch;

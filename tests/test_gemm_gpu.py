@@ -368,3 +368,25 @@ def test_fp32_presplit_operands(handle):
     assert r.ok and handle.last_presplit == 4                                             # kernel's splitters make bf16 tiles
     r = run_case(handle, Case(dtype="f32", m=512, n=512, k=65536, alpha=1.0, beta=0.0, env=(("PBX_F32_SPLIT16", "0"),)))
     assert r.ok and handle.last_presplit == 0                                             # 3xTF32 in-kernel split on request
+
+
+@pytest.mark.parametrize("dt", ["f32", "f64", "f16", "bf16f32"])
+def test_interleaved_through_the_strided_path(handle, dt):
+    """Large interleaved batches are re-laid out as strided batches (one pass each for A, B and -- when beta != 0 -- C),
+    run on the tensor-core path and written back interleaved (pbx_api.cu: interleaved_via_strided).  Same grid style as
+    the reference's interleaved suite (blas3_gemm_batched_test.cpp: all transposes, ld multipliers, offsets), batch
+    counts that are not multiples of the 32-entry transpose tiles, beta == 0 and != 0; the dedicated kernel must give
+    the same numbers when PBX_ILV_VIA_STRIDED=0 selects it."""
+    cases = []
+    for (ta, tb), (al, be) in itertools.product(TRANS, [(1.5, 0.0), (3.0, 7.0)]):
+        cases.append(Case(dtype=dt, api="batched", batch_type=1, transa=ta, transb=tb, m=136, n=72, k=200, alpha=al, beta=be,
+                          batch=70, env=(("PBX_ILV_VIA_STRIDED", "1"),)))
+    cases.append(Case(dtype=dt, api="batched", batch_type=1, m=63, n=129, k=65, alpha=3.0, beta=7.0, batch=33, offset=33,
+                      lda_mul=2, ldb_mul=3, ldc_mul=4, env=(("PBX_ILV_VIA_STRIDED", "1"),)))
+    cases.append(Case(dtype=dt, api="batched", batch_type=1, m=230, n=49, k=230, alpha=1.0, beta=0.0, batch=100))   # auto
+    _run_all(handle, cases)
+    r = run_case(handle, cases[-1])
+    assert r.ok and r.kernel != "interleaved", r
+    r = run_case(handle, Case(dtype=dt, api="batched", batch_type=1, m=230, n=49, k=230, alpha=1.0, beta=0.0, batch=100,
+                              env=(("PBX_ILV_VIA_STRIDED", "0"),)))
+    assert r.ok and r.kernel == "interleaved", r
