@@ -431,6 +431,7 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
   for (int x = 0; x < 7; ++x) tm.push.peer[x] = tm.a;
   p.tma_store = 0;
   p.push = 0;
+  p.push_pace = !(getenv("PBX_MULTICAST_PACE") && atoi(getenv("PBX_MULTICAST_PACE")) == 0);
   const bool out16 = (c.dtype == PBX_F16 || c.dtype == PBX_BF16);
   const char* ts_env = getenv("PBX_TMA_STORE");
   auto c_legal = [&](const void* ptr) {

@@ -69,8 +69,9 @@ struct TcParams {
   unsigned int* sched;
   int dynamic;
   // multicast GEMM, asynchronous form: the peer copies of a finished tile are pushed by TMA (see the pusher warp) instead
-  // of being stored by the epilogue warps
+  // of being stored by the epilogue warps; push_pace: spread a tile's peer stores over the next tile's duration
   int push;
+  int push_pace;
 };
 
 // tensor maps of the multicast GEMM's asynchronous peer copies: the local C (read back, 128 x 32 boxes) and the peers'
@@ -556,31 +557,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // NVLink except this lane: the accumulator is released as soon as the local stores are issued, so the transfer of
     // tile i runs under the mainloop of tile i+1 (round 1 stored to the peers from the epilogue warps: each tile's
     // 8 x 128 KiB burst had to drain through NVLink before the next MMA could start: 5.28 ms against 4.32 ms at 8 GPUs).
+    // Pacing: the per-SM TMA engine serves the producer's operand loads and these stores in order, so a burst of peer
+    // stores that NVLink cannot absorb at once (148 SMs x 7 peers x 128 KiB at the end of every round of tiles) holds
+    // up the loads behind it -- measured at 8 GPUs: +0.95 ms on 3.56 ms, i.e. the whole transfer time exposed although
+    // no warp waited for it.  The lane therefore spreads a tile's stores over about three quarters of the time the
+    // previous tile took (clock64 between tile completions); only a group's last tile goes out at full speed.
     if (lane == 0) {
       uint32_t handed = 0, ntile = 0, chunk = 0;
+      long long t_prev = clock64();
       for (int64_t tile = group; tile < p.total_tiles;) {
-        if (Cfg::PUSH_BYTES > 0 && p.push) {
-          const TileCoord tc = decode_tile(p, tile);
-          const int m0 = tc.mt * Cfg::TILE_M + (int)rank * BM;
-          const int n0 = tc.nt * BN;
-          const uint32_t target = (uint32_t)Cfg::EPI_WARPS * (ntile + 1u);
-          while (ld_acquire_shared_u32(push_count) < target) { }
-          for (int j = 0; j < BN / 32; ++j) {
-            if (n0 + 32 * j >= p.N || m0 >= p.M) break;
-            const uint32_t buf = chunk & 1u;
-            bulk_wait_read<1>();   // the stores that last used this box have read it
-            const uint32_t box = push_base + buf * Cfg::PUSH_BOX_BYTES;
-            mbar_expect_tx(pload_bar(buf), Cfg::PUSH_BOX_BYTES);
-            tma_load_3d(box, &tmPush.local, pload_bar(buf), m0, n0 + 32 * j, tc.b);
-            mbar_wait(pload_bar(buf), (chunk >> 1) & 1u);
-            for (int x = 0; x < p.n_extra; ++x) tma_store_3d(&tmPush.peer[x], box, m0, n0 + 32 * j, tc.b);
-            bulk_commit();
-            ++chunk;
-          }
-          ++ntile;
-        }
+        // the next tile first (it was published while this one was being loaded): is this the group's last one?
+        int64_t next;
         if (!p.dynamic) {
-          tile += num_groups;
+          next = tile + num_groups;
         } else {   // single lane: the consumer protocol without the warp-wide parts
           const int slot = (int)(handed % Cfg::SCHED_SLOTS);
           const uint32_t ph = (handed / Cfg::SCHED_SLOTS) & 1u;
@@ -590,8 +579,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           asm volatile("and.b32 %0, %1, 0;" : "=r"(dep) : "r"(v));
           if (CG == 2) mbar_arrive_remote(sempty_leader0 + 8u * slot + dep); else mbar_arrive(sempty_bar(slot) + dep);
           ++handed;
-          tile = (v == 0xFFFFFFFFu) ? p.total_tiles : (int64_t)v;
+          next = (v == 0xFFFFFFFFu) ? p.total_tiles : (int64_t)v;
         }
+        if (Cfg::PUSH_BYTES > 0 && p.push) {
+          const TileCoord tc = decode_tile(p, tile);
+          const int m0 = tc.mt * Cfg::TILE_M + (int)rank * BM;
+          const int n0 = tc.nt * BN;
+          const uint32_t target = (uint32_t)Cfg::EPI_WARPS * (ntile + 1u);
+          while (ld_acquire_shared_u32(push_count) < target) { }
+          const long long t_done = clock64();
+          const long long period = t_done - t_prev;   // first tile: since the kernel started
+          t_prev = t_done;
+          const bool last = next >= p.total_tiles;
+          const long long gap = (last || p.push_pace == 0) ? 0 : (period * 3 / 4) / ((BN / 32) * max(p.n_extra, 1));
+          for (int j = 0; j < BN / 32; ++j) {
+            if (n0 + 32 * j >= p.N || m0 >= p.M) break;
+            const uint32_t buf = chunk & 1u;
+            bulk_wait_read<1>();   // the stores that last used this box have read it
+            const uint32_t box = push_base + buf * Cfg::PUSH_BOX_BYTES;
+            mbar_expect_tx(pload_bar(buf), Cfg::PUSH_BOX_BYTES);
+            tma_load_3d(box, &tmPush.local, pload_bar(buf), m0, n0 + 32 * j, tc.b);
+            mbar_wait(pload_bar(buf), (chunk >> 1) & 1u);
+            for (int x = 0; x < p.n_extra; ++x) {
+              const long long t0 = clock64();
+              tma_store_3d(&tmPush.peer[x], box, m0, n0 + 32 * j, tc.b);
+              if (x + 1 == p.n_extra) bulk_commit();
+              while (clock64() - t0 < gap) __nanosleep(256);
+            }
+            ++chunk;
+          }
+          ++ntile;
+        }
+        tile = next;
       }
       if (Cfg::PUSH_BYTES > 0 && p.push) bulk_wait_all();   // every peer copy has left before the CTA retires
     }
