@@ -197,7 +197,6 @@ TcPlan make_plan(pbx_handle_t h, const PbxGemmCall& c) {
       if (c.n_extra == 0 && h->forced_split_k == 0 && kb >= 16) {
         smax = (2 * units) / tiles;
         if (smax > kb / 4) smax = kb / 4;
-        if (smax > 64) smax = 64;
         if (smax < 1) smax = 1;
       }
       for (int64_t sl = 1; sl <= smax; ++sl) {
