@@ -119,57 +119,40 @@ int64_t pbx_workspace_bytes(pbx_handle_t h) { return h ? h->ws_bytes : 0; }
 
 }  // extern "C"
 
-int pbx_ensure_workspace(pbx_handle_t h, int64_t bytes) {
-  if (bytes <= h->ws_bytes) return PBX_OK;
-  // The previous buffer may still be in use by work queued on the stream.
-  if (h->ws) {
-    if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaFree(h->ws) != cudaSuccess) {
-      h->last_error = "workspace free failed";
+// Pooled temporaries grow through the stream-ordered allocator: the old buffer is released and the new one obtained IN
+// stream order (cudaFreeAsync / cudaMallocAsync), so work already queued on the stream keeps its buffer and the call
+// stays asynchronous (round 1 synchronised the stream here, a hidden wait inside an "asynchronous" API).
+static int pbx_grow(pbx_handle_t h, void** buf, int64_t* cap, int64_t bytes, const char* what) {
+  if (bytes <= *cap) return PBX_OK;
+  if (*buf) {
+    if (cudaFreeAsync(*buf, h->stream) != cudaSuccess) {
+      cudaGetLastError();
+      h->last_error = std::string(what) + " free failed";
       return PBX_ERR_WORKSPACE;
     }
-    h->ws = nullptr; h->ws_bytes = 0;
+    *buf = nullptr; *cap = 0;
   }
   const int64_t rounded = ((bytes + (1 << 20) - 1) >> 20) << 20;
-  if (cudaMalloc(&h->ws, (size_t)rounded) != cudaSuccess) {
+  if (cudaMallocAsync(buf, (size_t)rounded, h->stream) != cudaSuccess) {
     cudaGetLastError();
-    h->last_error = "workspace allocation failed";
+    *buf = nullptr;
+    h->last_error = std::string(what) + " allocation failed";
     return PBX_ERR_WORKSPACE;
   }
-  h->ws_bytes = rounded;
+  *cap = rounded;
   return PBX_OK;
 }
 
+int pbx_ensure_workspace(pbx_handle_t h, int64_t bytes) { return pbx_grow(h, &h->ws, &h->ws_bytes, bytes, "workspace"); }
+
 int pbx_ensure_aux(pbx_handle_t h, int i, int64_t bytes) {
   if (i < 0 || i >= 4) return PBX_ERR_INVALID_ARG;
-  if (bytes <= h->aux_bytes[i]) return PBX_OK;
-  if (h->aux[i]) {
-    if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaFree(h->aux[i]) != cudaSuccess) {
-      h->last_error = "temporary free failed";
-      return PBX_ERR_WORKSPACE;
-    }
-    h->aux[i] = nullptr; h->aux_bytes[i] = 0;
-  }
-  const int64_t rounded = ((bytes + (1 << 20) - 1) >> 20) << 20;
-  if (cudaMalloc(&h->aux[i], (size_t)rounded) != cudaSuccess) {
-    cudaGetLastError();
-    h->last_error = "temporary allocation failed";
-    return PBX_ERR_WORKSPACE;
-  }
-  h->aux_bytes[i] = rounded;
-  return PBX_OK;
+  return pbx_grow(h, &h->aux[i], &h->aux_bytes[i], bytes, "temporary");
 }
 
 int pbx_ensure_lo(pbx_handle_t h, int i, int64_t bytes) {
   if (i < 0 || i >= 2) return PBX_ERR_INVALID_ARG;
-  if (bytes <= h->lo_bytes[i]) return PBX_OK;
-  if (h->lo[i]) {
-    if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaFree(h->lo[i]) != cudaSuccess) return PBX_ERR_WORKSPACE;
-    h->lo[i] = nullptr; h->lo_bytes[i] = 0;
-  }
-  const int64_t rounded = ((bytes + (1 << 20) - 1) >> 20) << 20;
-  if (cudaMalloc(&h->lo[i], (size_t)rounded) != cudaSuccess) { cudaGetLastError(); return PBX_ERR_WORKSPACE; }
-  h->lo_bytes[i] = rounded;
-  return PBX_OK;
+  return pbx_grow(h, &h->lo[i], &h->lo_bytes[i], bytes, "fp32 split copy");
 }
 
 // ---- split-K policy -------------------------------------------------------------
@@ -206,15 +189,7 @@ static int choose_split_k(pbx_handle_t h, const PbxGemmCall& c, int tile_m, int 
 // 16-byte-legal layout in a pooled buffer; the copy is one HBM-bound pass over that operand, after which
 // the call runs on the tensor cores instead of the CUDA-core kernel.
 static int ensure_pack(pbx_handle_t h, int i, int64_t bytes) {
-  if (bytes <= h->pack_bytes[i]) return PBX_OK;
-  if (h->pack[i]) {
-    if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaFree(h->pack[i]) != cudaSuccess) return PBX_ERR_WORKSPACE;
-    h->pack[i] = nullptr; h->pack_bytes[i] = 0;
-  }
-  const int64_t rounded = ((bytes + (1 << 20) - 1) >> 20) << 20;
-  if (cudaMalloc(&h->pack[i], (size_t)rounded) != cudaSuccess) { cudaGetLastError(); return PBX_ERR_WORKSPACE; }
-  h->pack_bytes[i] = rounded;
-  return PBX_OK;
+  return pbx_grow(h, &h->pack[i], &h->pack_bytes[i], bytes, "packed operand");
 }
 
 static bool repack_for_tma(pbx_handle_t h, PbxGemmCall& c) {
