@@ -792,7 +792,7 @@ int pbx_launch_splitk_reduce(pbx_handle_t h, const PbxGemmCall& c, int slices) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = h->pdl ? 1 : 0;
+    cfg.numAttrs = (h->pdl && h->pdl_reduce) ? 1 : 0;
     const TAcc* ws = (const TAcc*)h->ws;
     TOut* C = (TOut*)c.C;
     if (vec4)

@@ -64,6 +64,8 @@ int pbx_create(pbx_handle_t* out, int device_ordinal, void* cuda_stream) {
   if (ds) h->dynamic_sched = atoi(ds) != 0;
   const char* pdl = getenv("PBX_PDL");
   if (pdl) h->pdl = atoi(pdl) != 0;
+  const char* pdlr = getenv("PBX_PDL_REDUCE");
+  if (pdlr) h->pdl_reduce = atoi(pdlr) != 0;
   {
     PbxDeviceGuard guard(device_ordinal);
     if (!guard.ok() || cudaMalloc(&h->tile_sched, 256) != cudaSuccess ||

@@ -73,6 +73,7 @@ struct pbx_handle_s {
   unsigned int* tile_sched = nullptr;
   int dynamic_sched = 1;
   int pdl = 1;
+  int pdl_reduce = 1;   // PBX_PDL_REDUCE=0: the split-K reduce kernel alone is launched without the attribute
   PbxTmapCacheEntry tmap_cache[64];
   // staging buffers for pbx_gemm_host
   void* stage[3] = {nullptr, nullptr, nullptr};

@@ -32,12 +32,16 @@ VARIANTS = {
     "default": ({}, {}),
     "static": ({"PBX_DYNAMIC_SCHED": "0"}, {}),
     "nopdl": ({"PBX_PDL": "0"}, {}),
+    "nopdl_reduce": ({"PBX_PDL_REDUCE": "0"}, {}),
     "static_nopdl": ({"PBX_DYNAMIC_SCHED": "0", "PBX_PDL": "0"}, {}),
     "cg2_256": ({}, {"PBX_TC_CONFIG": "2,256"}),
     "cg2_128": ({}, {"PBX_TC_CONFIG": "2,128"}),
     "cg1_128": ({}, {"PBX_TC_CONFIG": "1,128"}),
     "static_cg2_256": ({"PBX_DYNAMIC_SCHED": "0"}, {"PBX_TC_CONFIG": "2,256"}),
     "split16_off": ({}, {"PBX_F32_SPLIT16": "0"}),
+    "chunk32": ({}, {"PBX_TF32_CHUNK_KB": "32"}),      # timing probes only: longer tensor-core accumulation chains
+    "chunk64": ({}, {"PBX_TF32_CHUNK_KB": "64"}),      # exceed the fp32 error budget
+    "chunk_inf": ({}, {"PBX_TF32_CHUNK_KB": "1000000"}),
     "presplit_off": ({}, {"PBX_TF32_PRESPLIT": "0"}),
 }
 
@@ -66,8 +70,14 @@ def main():
     ap.add_argument("--rounds", type=int, default=9)
     ap.add_argument("--rest", type=float, default=0.4)
     ap.add_argument("--sustained-s", type=float, default=0.6)
+    ap.add_argument("--shape", default="", help="dtype,m,n,k[,batch]: an ad-hoc NN problem instead of a bench.py workload")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
+    if args.shape:
+        f = args.shape.split(",")
+        w = dict(dt=f[0], m=int(f[1]), n=int(f[2]), k=int(f[3]), batch=int(f[4]) if len(f) > 4 else 1, ta="n", tb="n", alpha=1.0,
+                 beta=0.0)
+        args.workload = args.shape
     dev = torch.device("cuda", 0)
     tdt = {"f64": torch.float64, "f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}[w["dt"]]
     m, n, k, batch = w["m"], w["n"], w["k"], w["batch"]
