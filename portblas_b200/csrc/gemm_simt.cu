@@ -792,7 +792,11 @@ int pbx_launch_splitk_reduce(pbx_handle_t h, const PbxGemmCall& c, int slices) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = (h->pdl && h->pdl_reduce) ? 1 : 0;
+    // Programmatic launch lets this grid become resident while the GEMM drains -- a gain when the GEMM leaves SMs free
+    // (SGEMM 1024^3: 19.3 -> 18.1 us), a loss when it fills the machine (64 x 147 x 13225 on 206 CTAs: 35 -> 46 us), so
+    // it is requested only behind a tcgen05 grid smaller than the SM count
+    cfg.numAttrs = (h->pdl && h->pdl_reduce && h->last_grid_ctas < h->sm_count) ? 1 : 0;
+    h->last_grid_ctas = 1 << 30;
     const TAcc* ws = (const TAcc*)h->ws;
     TOut* C = (TOut*)c.C;
     if (vec4)

@@ -150,7 +150,12 @@ struct TcCfg {
   static constexpr int RAW_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGE_BYTES = RAW_BYTES * ((TF32X3 && PRE != 2) ? 2 : 1);  // + lo copies
   static constexpr int BAR_BYTES = 512;
-  static constexpr int EPI_WARPS = 8;
+  // Warp budget after the four role warps: 8 epilogue warps (4 TMEM lane quarters x 2 column halves), or -- in the
+  // in-kernel split modes -- 4 epilogue warps and 8 splitter warps.  The splitters are the slower side there: one warp per
+  // scheduler issued ~440 dependent-ish instructions per K block (0.8 us against 0.54 us of MMA time); two warps per
+  // scheduler hide each other's latencies, and the epilogue only works at chunk and tile ends.
+  static constexpr bool SPLIT_MODE = (ES == 4) && (PRE == 0 || PRE == 4);
+  static constexpr int EPI_WARPS = SPLIT_MODE ? 4 : 8;
   // 16-bit outputs: every epilogue warp owns two 32x32 staging tiles (column-major, rows contiguous)
   // that it hands to TMA stores, so C leaves the SM as bulk writes instead of 2-byte stores
   static constexpr int EPI_TILE_BYTES = 32 * 32 * OS;
@@ -175,7 +180,7 @@ struct TcCfg {
   static constexpr int ACC_STAGES = TF32X3 ? ((3 * BN <= 512) ? 2 : 1) : 2;
   static constexpr int RSUM_COL = ACC_STAGES * BN;
   static constexpr int TMEM_COLS = TF32X3 ? 512 : 2 * BN;
-  static constexpr int SPLIT_WARPS = (TF32X3 && (PRE == 0 || PRE == 4)) ? 4 : 0;
+  static constexpr int SPLIT_WARPS = SPLIT_MODE ? 8 : 0;
   static constexpr int TMA_BYTES = RAW_BYTES * ((TF32X3 && (PRE == 1 || PRE == 3)) ? 2 : 1);   // bytes one CTA's producer lands per stage
   static constexpr int NUM_THREADS = 32 * (4 + EPI_WARPS + SPLIT_WARPS);
   static constexpr int NUM_SPLIT_THREADS = 32 * SPLIT_WARPS;
@@ -619,7 +624,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves =====================
     const int ew = warp & 3;           // TMEM lane quarter this warp may read
     const int ch = (warp - 4) >> 2;    // column half
-    constexpr int COLS_PER_WARP = BN / 2;
+    constexpr int COLS_PER_WARP = BN / (Cfg::EPI_WARPS / 4);   // column groups = epilogue warps per lane quarter
     constexpr bool OUT16 = (sizeof(TOut) == 2);
     const bool beta0 = (p.beta == 0.0f);
     const bool tma_store = OUT16 && p.tma_store;
@@ -1020,6 +1025,7 @@ int launch_inst(pbx_handle_t h, const TcMaps& tm, const TcParams& p_in) {
   cfg.attrs = attr;
   cfg.numAttrs = h->pdl ? 2 : 1;
   PBX_CUDA_CHECK(h, cudaLaunchKernelEx(&cfg, kern, tm.a, tm.b, tm.c, tm.alo, tm.blo, tm.push, p));
+  h->last_grid_ctas = (int)(groups * CG);
   h->launches++;
   return PBX_OK;
 }

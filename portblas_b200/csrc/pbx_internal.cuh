@@ -74,6 +74,7 @@ struct pbx_handle_s {
   int dynamic_sched = 1;
   int pdl = 1;
   int pdl_reduce = 1;   // PBX_PDL_REDUCE=0: the split-K reduce kernel alone is launched without the attribute
+  int last_grid_ctas = 1 << 30;   // CTAs of the last tcgen05 launch (the reduce kernel rides along only when SMs are free)
   PbxTmapCacheEntry tmap_cache[64];
   // staging buffers for pbx_gemm_host
   void* stage[3] = {nullptr, nullptr, nullptr};
