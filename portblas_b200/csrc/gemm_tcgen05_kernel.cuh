@@ -150,12 +150,12 @@ struct TcCfg {
   static constexpr int RAW_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGE_BYTES = RAW_BYTES * ((TF32X3 && PRE != 2) ? 2 : 1);  // + lo copies
   static constexpr int BAR_BYTES = 512;
-  // Warp budget after the four role warps: 8 epilogue warps (4 TMEM lane quarters x 2 column halves), or -- in the
-  // in-kernel split modes -- 4 epilogue warps and 8 splitter warps.  The splitters are the slower side there: one warp per
-  // scheduler issued ~440 dependent-ish instructions per K block (0.8 us against 0.54 us of MMA time); two warps per
-  // scheduler hide each other's latencies, and the epilogue only works at chunk and tile ends.
+  // Warp budget after the four role warps: 8 epilogue warps (4 TMEM lane quarters x 2 column halves) and, in the
+  // in-kernel split modes, 4 splitter warps.  (4 epilogue + 8 splitter warps were measured in round 2: no gain -- SGEMM
+  // 512 x 512 x 2^20 302.8 vs 300.7 TFLOP/s, 384 x 5408 x 3456 173 vs 181 -- the split modes are bound by shared-memory
+  // bandwidth, ~160 KB per K block and SM against 128 B/clk, not by the splitters' issue rate.)
   static constexpr bool SPLIT_MODE = (ES == 4) && (PRE == 0 || PRE == 4);
-  static constexpr int EPI_WARPS = SPLIT_MODE ? 4 : 8;
+  static constexpr int EPI_WARPS = 8;
   // 16-bit outputs: every epilogue warp owns two 32x32 staging tiles (column-major, rows contiguous)
   // that it hands to TMA stores, so C leaves the SM as bulk writes instead of 2-byte stores
   static constexpr int EPI_TILE_BYTES = 32 * 32 * OS;
@@ -180,7 +180,7 @@ struct TcCfg {
   static constexpr int ACC_STAGES = TF32X3 ? ((3 * BN <= 512) ? 2 : 1) : 2;
   static constexpr int RSUM_COL = ACC_STAGES * BN;
   static constexpr int TMEM_COLS = TF32X3 ? 512 : 2 * BN;
-  static constexpr int SPLIT_WARPS = SPLIT_MODE ? 8 : 0;
+  static constexpr int SPLIT_WARPS = SPLIT_MODE ? 4 : 0;
   static constexpr int TMA_BYTES = RAW_BYTES * ((TF32X3 && (PRE == 1 || PRE == 3)) ? 2 : 1);   // bytes one CTA's producer lands per stage
   static constexpr int NUM_THREADS = 32 * (4 + EPI_WARPS + SPLIT_WARPS);
   static constexpr int NUM_SPLIT_THREADS = 32 * SPLIT_WARPS;
