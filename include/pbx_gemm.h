@@ -103,7 +103,9 @@ int pbx_synchronize(pbx_handle_t h);               /* SB_Handle::wait() */
 const char* pbx_last_error(pbx_handle_t h);        /* text of the last failure (may be "") */
 const char* pbx_status_string(int status);         /* the reference's exception text for a status */
 
-/* Testing / tuning hooks. */
+/* Testing / tuning hooks.  The PBX_* environment switches (DESIGN.md lists them) are read by pbx_create and again by
+ * pbx_reload_env; a GEMM call itself reads only SB_ENABLE_JOINT_MATRIX, the variable the reference reads per call. */
+int pbx_reload_env(pbx_handle_t h);
 int pbx_set_forced_kernel(pbx_handle_t h, int kernel /* pbx_kernel_t */);
 int pbx_set_split_k(pbx_handle_t h, int slices /* 0 = auto, 1 = never, >1 = force */);
 int pbx_last_kernel(pbx_handle_t h);               /* pbx_kernel_t used by the last call */

@@ -32,6 +32,7 @@ SYMBOLS = {
     "pbx_synchronize": (c_int, [c_void_p]),
     "pbx_last_error": (c_char_p, [c_void_p]),
     "pbx_status_string": (c_char_p, [c_int]),
+    "pbx_reload_env": (c_int, [c_void_p]),
     "pbx_set_forced_kernel": (c_int, [c_void_p, c_int]),
     "pbx_set_split_k": (c_int, [c_void_p, c_int]),
     "pbx_last_kernel": (c_int, [c_void_p]),

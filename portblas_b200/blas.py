@@ -100,6 +100,10 @@ class SB_Handle:
         _check(self, self._lib.pbx_set_stream(self._h, ctypes.c_void_p(sptr)))
 
     # -- testing / tuning hooks -----------------------------------------------------------------
+    def reload_env(self) -> None:
+        """Re-read the PBX_* switches from the environment (they are read once when the handle is created)."""
+        _check(self, self._lib.pbx_reload_env(self._h))
+
     def set_forced_kernel(self, kernel: int) -> None:
         _check(self, self._lib.pbx_set_forced_kernel(self._h, int(kernel)))
 

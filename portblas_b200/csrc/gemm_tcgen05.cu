@@ -164,15 +164,15 @@ TcPlan make_plan(pbx_handle_t h, const PbxGemmCall& c) {
   };
   auto usable = [&](const Cand& cd) { return !(cd.cg == 2 && c.m <= 128) && !(cd.bn == 256 && c.n <= 128); };
   TcPlan plan = {1, 128, 1, false};
-  const char* swap_env = getenv("PBX_TC_SWAP");   // "0" disables the skinny-M operand swap (testing)
-  const bool want_swap = c.m <= 64 && c.n > c.m && !(swap_env && atoi(swap_env) == 0) && c.n_extra == 0;
-  const char* force = getenv("PBX_TC_CONFIG");  // "cg,bn" (testing)
-  int fcg = 0, fbn = 0;
-  if (force && sscanf(force, "%d,%d", &fcg, &fbn) == 2 && (fcg == 1 || fcg == 2) && (fbn == 128 || (fbn == 256 && fcg == 2))) {
+  const PbxKnobs& kn = h->knobs;
+  const bool want_swap = c.m <= 64 && c.n > c.m && kn.tc_swap != 0 && c.n_extra == 0;
+  const int fcg = kn.tc_cg, fbn = kn.tc_bn;   // PBX_TC_CONFIG (testing)
+  const bool force = (fcg == 1 || fcg == 2) && (fbn == 128 || (fbn == 256 && fcg == 2));
+  if (force) {
     plan.cg = fcg; plan.bn = fbn;
   } else if (want_swap) {
     plan.cg = 1; plan.bn = 64; plan.swap = true;
-  } else if (!(getenv("PBX_PLAN_MODEL") && atoi(getenv("PBX_PLAN_MODEL")) == 0)) {
+  } else if (kn.plan_model != 0) {
     // Cost model (round 2; replaces the ">= 0.6 of a wave" threshold, which left 1.16-wave schedules and rejected
     // 0.59-wave ones: 384 x 5408 x 3456 ran at 53 TFLOP/s on 86 half-tiles in two rounds).  For every tile
     // configuration and K-slice count the duration is estimated in units of one K block of a CTA pair on a 256x256 tile:
@@ -237,7 +237,7 @@ TcPlan make_plan(pbx_handle_t h, const PbxGemmCall& c) {
   // schedule the pairs win (round 2, same box, burst: 548 vs 490 TFLOP/s = 6.42 vs 5.74 TB/s; cuBLAS 571): a 256x256
   // tile loads every operand byte exactly once, while the four 128x128 tiles of a batch entry load each panel twice
   // and lean on L2 to merge the copies (ncu: L2 hit rate 47 %, i.e. half of the load traffic is duplicate).
-  if (!(force && fcg) && !plan.swap && pbx_in_size(c.dtype) == 2 && !h->dynamic_sched) {
+  if (!force && !plan.swap && pbx_in_size(c.dtype) == 2 && !h->dynamic_sched) {
     const double flops = 2.0 * (double)c.m * (double)c.n * (double)c.k;
     const double byts = 2.0 * ((double)c.m * c.k + (double)c.k * c.n) + (double)pbx_out_size(c.dtype) * c.m * c.n;
     const Cand small = {1, 128};
@@ -335,7 +335,7 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
   const char* jm_env = getenv("SB_ENABLE_JOINT_MATRIX");
   const bool tf32x1 = f32 && jm_env != nullptr && jm_env[0] == '1';
   if (f32 && !tf32x1) {
-    const int pre_env = getenv("PBX_TF32_PRESPLIT") ? atoi(getenv("PBX_TF32_PRESPLIT")) : -1;
+    const int pre_env = h->knobs.tf32_presplit;
     const double flops = 2.0 * (double)c.m * (double)c.n * (double)c.k * (double)c.batch;
     const double byts = 4.0 * ((double)c.m * c.k + (double)c.k * c.n + (double)c.m * c.n) * (double)c.batch;
     pre = (pre_env >= 0) ? (pre_env != 0) : (flops >= 5e8 && flops / byts >= 256.0);
@@ -343,8 +343,7 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
     // fp32 lo pre-split on the shapes that would get it; same pooled buffers (2 x 2 bytes per element instead of 4),
     // the copies laid out [hi of every batch entry | lo of every batch entry].  Measured on B200 (round 2): SGEMM
     // 8192^3 270 -> 329 TFLOP/s, 16384^3 (power-capped) 197 -> 257, same <= 1e-5 error bound.
-    const char* s16_env = getenv("PBX_F32_SPLIT16");
-    if (pre && !(s16_env != nullptr && s16_env[0] == '0')) {
+    if (pre && h->knobs.f32_split16 != 0) {
       split16 = true;
       const Opnd* ops[2] = {&X, &Y};
       for (int i = 0; i < 2 && split16; ++i) {
@@ -395,8 +394,7 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
   }
   // no pre-pass: the splitter warps of the kernel make the lo halves -- as bf16 tiles (mode 4: tf32 + 2 x bf16, two
   // tf32-MMA times per k-step) unless PBX_F32_SPLIT16=0 asks for the 3xTF32 form (mode 0)
-  const char* s16_off = getenv("PBX_F32_SPLIT16");
-  const bool inkernel16 = f32 && !tf32x1 && !pre && !(s16_off != nullptr && s16_off[0] == '0');
+  const bool inkernel16 = f32 && !tf32x1 && !pre && h->knobs.f32_split16 != 0;
   const int pre_mode = tf32x1 ? 2 : (split16 ? 3 : (pre ? 1 : (inkernel16 ? 4 : 0)));
   h->last_presplit = pre_mode;
   TcParams p;
@@ -411,11 +409,10 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
   p.kb_per_slice = (p.kb_total + slices - 1) / slices;
   // fp32: the tensor core truncates when it adds into its fp32 accumulator, so an accumulation
   // chain is limited to kb_per_chunk blocks of 32 (default 16 -> 512 k: ~4e-6 relative bias)
-  const int chunk_env = getenv("PBX_TF32_CHUNK_KB") ? atoi(getenv("PBX_TF32_CHUNK_KB")) : 0;
+  const int chunk_env = h->knobs.tf32_chunk_kb;
   p.kb_per_chunk = f32 ? (chunk_env > 0 ? chunk_env : 16) : (1 << 30);
   // default: raw fp32 tile as the hi operand (verified on B200: kind::tf32 ignores the low 13 mantissa bits)
-  const int raw_hi_env = getenv("PBX_TF32_RAW_HI") ? atoi(getenv("PBX_TF32_RAW_HI")) : 1;
-  p.raw_hi = raw_hi_env;
+  p.raw_hi = h->knobs.tf32_raw_hi;
   p.a_batched = (c.batch > 1 && X.st > 0) ? 1 : 0;
   p.b_batched = (c.batch > 1 && Y.st > 0) ? 1 : 0;
   const int64_t eo = (int64_t)pbx_out_size(c.dtype);
@@ -430,16 +427,16 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
   for (int x = 0; x < 7; ++x) tm.push.peer[x] = tm.a;
   p.tma_store = 0;
   p.push = 0;
-  p.push_pace = !(getenv("PBX_MULTICAST_PACE") && atoi(getenv("PBX_MULTICAST_PACE")) == 0);
+  p.push_pace = h->knobs.multicast_pace;
+  p.wait_hint_ns = h->knobs.wait_hint_ns;
   const bool out16 = (c.dtype == PBX_F16 || c.dtype == PBX_BF16);
-  const char* ts_env = getenv("PBX_TMA_STORE");
   auto c_legal = [&](const void* ptr) {
     return ((uintptr_t)ptr % 16 == 0) && (c.ldc * eo) % 16 == 0 && (c.batch == 1 || (c.sc * eo) % 16 == 0) &&
            c.ldc * eo < ((int64_t)1 << 40) && c.sc * eo < ((int64_t)1 << 40);
   };
   bool peers_legal = true;
   for (int x = 0; x < c.n_extra; ++x) peers_legal = peers_legal && c_legal(c.c_extra[x]);
-  if (out16 && c.beta == 0.0 && slices == 1 && !(ts_env && atoi(ts_env) == 0) && c_legal(c.C) &&
+  if (out16 && c.beta == 0.0 && slices == 1 && h->knobs.tma_store != 0 && c_legal(c.C) &&
       peers_legal) {
     bool ok = make_c_map(h, &tm.c, 2, dt, c.C, c.m, c.n, c.ldc, c.batch, c.sc);
     // multicast GEMM: the staging tiles of the TMA-store epilogue also go to every peer's C
@@ -448,8 +445,7 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
   }
   // multicast GEMM with 32-bit outputs: asynchronous peer copies by the pusher warp (128 x 32 boxes read back from the
   // local C); PBX_MULTICAST_PUSH=0 keeps the round-1 form (the epilogue warps store to every copy themselves)
-  const char* push_env = getenv("PBX_MULTICAST_PUSH");
-  if (c.n_extra > 0 && eo == 4 && slices == 1 && !plan.swap && !(push_env && atoi(push_env) == 0) && c_legal(c.C) && peers_legal) {
+  if (c.n_extra > 0 && eo == 4 && slices == 1 && !plan.swap && h->knobs.multicast_push != 0 && c_legal(c.C) && peers_legal) {
     bool ok = make_c_map(h, &tm.push.local, 4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, c.C, c.m, c.n, c.ldc, c.batch, c.sc, BM);
     for (int x = 0; x < c.n_extra && ok; ++x)
       ok = make_c_map(h, &tm.push.peer[x], 4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, c.c_extra[x], c.m, c.n, c.ldc, c.batch, c.sc, BM);

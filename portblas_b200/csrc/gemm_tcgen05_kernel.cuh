@@ -72,6 +72,7 @@ struct TcParams {
   // of being stored by the epilogue warps; push_pace: spread a tile's peer stores over the next tile's duration
   int push;
   int push_pace;
+  unsigned int wait_hint_ns;   // suspend-time hint of the long mbarrier waits (0 = the instruction's default)
 };
 
 // tensor maps of the multicast GEMM's asynchronous peer copies: the local C (read back, 128 x 32 boxes) and the peers'
@@ -345,7 +346,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_slice);
         const int za = p.a_batched ? tc.b : 0, zb = p.b_batched ? tc.b : 0;
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_wait(empty_bar(stage), phase ^ 1u, p.wait_hint_ns);
           const uint32_t sA = smem_base + stage * Cfg::RAW_STRIDE;
           const uint32_t sB = sA + Cfg::A_BYTES;
           const uint32_t fb = full_bar(stage);
@@ -485,7 +486,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // in-kernel split: the derived stage is complete once every splitter thread has arrived (they waited for
             // the raw stage's TMA first); in pair mode the peer's splitter warps wrote shared memory with ordinary stores
             if (kSplit) { if (CG == 2) mbar_wait_cluster(split_bar(dstage), dphase); else mbar_wait(split_bar(dstage), dphase); }
-            else mbar_wait(full_bar(stage), phase);
+            else mbar_wait(full_bar(stage), phase, p.wait_hint_ns);
             tc_fence_after();
             const uint32_t sA = smem_base + stage * Cfg::RAW_STRIDE;
             const uint32_t sB = sA + Cfg::A_BYTES;
@@ -648,7 +649,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool first = (kc0 == kb0), last = (kc0 + p.kb_per_chunk >= kb1);
         const int as = it % ACC_STAGES;
         const uint32_t aphase = (uint32_t)(it / ACC_STAGES) & 1u;
-        mbar_wait(tfull_bar(as), aphase);
+        mbar_wait(tfull_bar(as), aphase, p.wait_hint_ns);
         tc_fence_after();
         const uint32_t t_lane = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ch * COLS_PER_WARP);
         const uint32_t t_row = t_lane + (uint32_t)(as * BN);

@@ -60,12 +60,7 @@ int pbx_create(pbx_handle_t* out, int device_ordinal, void* cuda_stream) {
   h->cc_minor = prop.minor;
   const char* fk = getenv("PBX_FORCE_KERNEL");
   if (fk) h->forced_kernel = atoi(fk);
-  const char* ds = getenv("PBX_DYNAMIC_SCHED");
-  if (ds) h->dynamic_sched = atoi(ds) != 0;
-  const char* pdl = getenv("PBX_PDL");
-  if (pdl) h->pdl = atoi(pdl) != 0;
-  const char* pdlr = getenv("PBX_PDL_REDUCE");
-  if (pdlr) h->pdl_reduce = atoi(pdlr) != 0;
+  pbx_reload_env(h);
   {
     PbxDeviceGuard guard(device_ordinal);
     if (!guard.ok() || cudaMalloc(&h->tile_sched, 256) != cudaSuccess ||
@@ -75,6 +70,32 @@ int pbx_create(pbx_handle_t* out, int device_ordinal, void* cuda_stream) {
     }
   }
   *out = h;
+  return PBX_OK;
+}
+
+// (Re-)read the PBX_* testing / tuning switches into the handle.  pbx_create calls it; a caller that changes the
+// environment afterwards (the test-suite does, per case) calls it again.
+int pbx_reload_env(pbx_handle_t h) {
+  if (!h) return PBX_ERR_INVALID_ARG;
+  auto geti = [](const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; };
+  PbxKnobs k;
+  k.tc_swap = geti("PBX_TC_SWAP", 1);
+  const char* cfg = getenv("PBX_TC_CONFIG");
+  if (!(cfg && sscanf(cfg, "%d,%d", &k.tc_cg, &k.tc_bn) == 2)) { k.tc_cg = 0; k.tc_bn = 0; }
+  k.plan_model = geti("PBX_PLAN_MODEL", 1);
+  k.tf32_presplit = geti("PBX_TF32_PRESPLIT", -1);
+  k.f32_split16 = geti("PBX_F32_SPLIT16", 1);
+  k.tf32_chunk_kb = geti("PBX_TF32_CHUNK_KB", 0);
+  k.tf32_raw_hi = geti("PBX_TF32_RAW_HI", 1);
+  k.multicast_pace = geti("PBX_MULTICAST_PACE", 1);
+  k.multicast_push = geti("PBX_MULTICAST_PUSH", 1);
+  k.wait_hint_ns = (unsigned)geti("PBX_WAIT_HINT_NS", 0);
+  k.tma_store = geti("PBX_TMA_STORE", 1);
+  k.ilv_via_strided = geti("PBX_ILV_VIA_STRIDED", -1);
+  h->knobs = k;
+  h->dynamic_sched = geti("PBX_DYNAMIC_SCHED", 1) != 0;
+  h->pdl = geti("PBX_PDL", 1) != 0;
+  h->pdl_reduce = geti("PBX_PDL_REDUCE", 1) != 0;
   return PBX_OK;
 }
 
@@ -227,7 +248,7 @@ static int run_gemm(pbx_handle_t h, const PbxGemmCall& c_in, int batch_type);
 // extra passes cost about twice the algorithmic bytes.  Taken when the batch is large enough to fill the transposes'
 // 32-entry tiles and the matrices are not tiny; PBX_ILV_VIA_STRIDED=0 keeps the dedicated kernel.
 static bool interleaved_via_strided(pbx_handle_t h, const PbxGemmCall& c, int* status) {
-  const int env = getenv("PBX_ILV_VIA_STRIDED") ? atoi(getenv("PBX_ILV_VIA_STRIDED")) : -1;   // 0 never, 1 always (testing)
+  const int env = h->knobs.ilv_via_strided;   // PBX_ILV_VIA_STRIDED: 0 never, 1 always (testing)
   if (env == 0) return false;
   if (h->forced_kernel == PBX_KERNEL_INTERLEAVED) return false;
   const double flops = 2.0 * (double)c.m * (double)c.n * (double)c.k * (double)c.batch;

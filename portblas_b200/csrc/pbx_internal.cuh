@@ -39,6 +39,24 @@ struct PbxTmapCacheEntry {
   bool valid = false;
 };
 
+// Testing / tuning switches (PBX_* environment variables).  They are read when the handle is created and again by
+// pbx_reload_env(): a GEMM call itself reads one variable only, SB_ENABLE_JOINT_MATRIX -- the one the reference reads
+// per call (src/interface/blas3/backend/nvidia_gpu.hpp:68-69).
+struct PbxKnobs {
+  int tc_swap = 1;            // PBX_TC_SWAP=0: no skinny-M operand swap
+  int tc_cg = 0, tc_bn = 0;   // PBX_TC_CONFIG="cg,bn": forced tile configuration
+  int plan_model = 1;         // PBX_PLAN_MODEL=0: round 1's threshold planner
+  int tf32_presplit = -1;     // PBX_TF32_PRESPLIT=0/1: never / always a pre-pass for the fp32 lo halves (-1: by shape)
+  int f32_split16 = 1;        // PBX_F32_SPLIT16=0: the 3xTF32 forms instead of tf32 + 2 x bf16
+  int tf32_chunk_kb = 0;      // PBX_TF32_CHUNK_KB: K blocks per tensor-core accumulation chain (0: 16)
+  int tf32_raw_hi = 1;        // PBX_TF32_RAW_HI=0: rounded tf32 hi operand instead of the raw fp32 tile
+  int multicast_pace = 1;     // PBX_MULTICAST_PACE=0: the pusher sends a tile's peer copies at once
+  int multicast_push = 1;     // PBX_MULTICAST_PUSH=0: peer copies stored by the epilogue warps (round 1)
+  unsigned wait_hint_ns = 0;  // PBX_WAIT_HINT_NS: suspend-time hint of the long mbarrier waits (measured: no gain)
+  int tma_store = 1;          // PBX_TMA_STORE=0: 16-bit C by direct stores
+  int ilv_via_strided = -1;   // PBX_ILV_VIA_STRIDED=0/1: never / always re-lay interleaved batches out (-1: by shape)
+};
+
 struct pbx_handle_s {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -76,6 +94,7 @@ struct pbx_handle_s {
   int pdl_reduce = 1;   // PBX_PDL_REDUCE=0: the split-K reduce kernel alone is launched without the attribute
   int last_grid_ctas = 1 << 30;   // CTAs of the last tcgen05 launch (the reduce kernel rides along only when SMs are free)
   PbxTmapCacheEntry tmap_cache[64];
+  PbxKnobs knobs;
   // staging buffers for pbx_gemm_host
   void* stage[3] = {nullptr, nullptr, nullptr};
   int64_t stage_bytes[3] = {0, 0, 0};

@@ -30,15 +30,28 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// hint_ns > 0: upper bound (nanoseconds) the hardware may keep the thread suspended inside ONE try_wait before it
+// returns false and the loop polls again; completion of the phase wakes it at once either way.  A longer suspension
+// means fewer polling instructions from the warps that wait most of the time (epilogue warps between accumulators).
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t hint_ns = 0) {
   uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  } while (!ok);
+  if (hint_ns == 0) {
+    do {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+  } else {
+    do {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok) : "r"(bar), "r"(parity), "r"(hint_ns) : "memory");
+    } while (!ok);
+  }
 }
 // generic-proxy writes (st.shared) -> visible to the async proxy (tcgen05.mma / TMA)
 __device__ __forceinline__ void fence_proxy_async() {

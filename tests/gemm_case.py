@@ -159,6 +159,8 @@ def run_case(handle: blas.SB_Handle, cs: Case) -> Result:
     saved_env = {name: os.environ.get(name) for name, _ in cs.env}
     for name, val in cs.env:
         os.environ[name] = str(val)
+    if cs.env:
+        handle.reload_env()   # the PBX_* switches are read into the handle, not per call
     status_text = ""
     try:
         if cs.api == "gemm":
@@ -181,6 +183,8 @@ def run_case(handle: blas.SB_Handle, cs: Case) -> Result:
                 os.environ.pop(name, None)
             else:
                 os.environ[name] = old
+        if cs.env:
+            handle.reload_env()
     kern, sk = handle.last_kernel, handle.last_split_k
     if st_exp != 0 or status_text:
         ok = oracle.STATUS_TEXT.get(st_exp, "?") == status_text

@@ -30,12 +30,16 @@ TD = {"f32": (torch.float32, torch.float32, 2e-5), "f64": (torch.float64, torch.
 
 
 class _Env:
-    def __init__(self, **kv):
+    """Environment switches around a call; the handle re-reads them (they are not read per call)."""
+
+    def __init__(self, handle, **kv):
+        self.handle = handle
         self.kv = {k: str(v) for k, v in kv.items()}
 
     def __enter__(self):
         self.old = {k: os.environ.get(k) for k in self.kv}
         os.environ.update(self.kv)
+        self.handle.reload_env()
 
     def __exit__(self, *a):
         for k, v in self.old.items():
@@ -43,6 +47,7 @@ class _Env:
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
+        self.handle.reload_env()
 
 
 def _operands(dt, ta, tb, m, n, k, batch, dev, seed=7):
@@ -121,7 +126,7 @@ def test_beta_zero_never_reads_c(handle, case, poison):
     handle.set_forced_kernel(kernel)
     handle.set_split_k(sk if sk > 1 else 0)
     try:
-        with _Env(**env):
+        with _Env(handle, **env):
             if batch == 1:
                 blas._gemm(handle, ta, tb, m, n, k, 1.5, a.view(-1), lda, b.view(-1), ldb, 0.0, c, ldc)
             else:

@@ -5,8 +5,8 @@ torch.matmul) in ONE process, interleaved, in two regimes:
               the median round is reported
   sustained : back-to-back launches for `--sustained-s` seconds (the board settles at its power cap)
 
-Variants are handles created under different environment switches (PBX_DYNAMIC_SCHED, PBX_PDL are read by pbx_create;
-PBX_TC_CONFIG and the other per-call switches are set around each call).  Measurement aid only.
+Variants are handles created under different environment switches (every PBX_* switch is read into the handle by
+pbx_create).  Measurement aid only.
 
     python tools/ab_variants.py --workload bf16gemm_batched > gpurun_out/ab_cfg4.jsonl
 """
@@ -43,6 +43,9 @@ VARIANTS = {
     "chunk64": ({}, {"PBX_TF32_CHUNK_KB": "64"}),      # exceed the fp32 error budget
     "chunk_inf": ({}, {"PBX_TF32_CHUNK_KB": "1000000"}),
     "presplit_off": ({}, {"PBX_TF32_PRESPLIT": "0"}),
+    "hint1us": ({}, {"PBX_WAIT_HINT_NS": "1000"}),
+    "hint20us": ({}, {"PBX_WAIT_HINT_NS": "20000"}),
+    "hint1ms": ({}, {"PBX_WAIT_HINT_NS": "1000000"}),
 }
 
 
@@ -95,16 +98,15 @@ def main():
             runners[name] = run
             continue
         create_env, call_env = VARIANTS[name]
-        with Env(create_env):
+        with Env({**create_env, **call_env}):   # every PBX_* switch is read into the handle when it is created
             h = SB_Handle(0)
 
-        def run(h=h, call_env=call_env):
-            with Env(call_env):
-                if batch == 1:
-                    blas._gemm(h, w["ta"], w["tb"], m, n, k, w["alpha"], a, m, b, k, w["beta"], c, m)
-                else:
-                    blas._gemm_strided_batched(h, w["ta"], w["tb"], m, n, k, w["alpha"], a, m, m * k, b, k, k * n, w["beta"], c, m,
-                                               m * n, batch)
+        def run(h=h):
+            if batch == 1:
+                blas._gemm(h, w["ta"], w["tb"], m, n, k, w["alpha"], a, m, b, k, w["beta"], c, m)
+            else:
+                blas._gemm_strided_batched(h, w["ta"], w["tb"], m, n, k, w["alpha"], a, m, m * k, b, k, k * n, w["beta"], c, m,
+                                           m * n, batch)
         runners[name] = run
     for run in runners.values():
         for _ in range(3):

@@ -55,6 +55,7 @@ def main():
             return best
 
         os.environ.pop("PBX_TC_CONFIG", None)
+        h.reload_env()
         h.set_split_k(0)
         t = timed()
         print(json.dumps(dict(m=m, n=n, k=k, dtype=args.dtype, cfg="auto", slices=h.last_split_k, presplit=h.last_presplit,
@@ -69,11 +70,13 @@ def main():
                            if s <= max(1, kb // 4) and tiles * s <= 4 * units})
             for s in cand:
                 os.environ["PBX_TC_CONFIG"] = cfg
+                h.reload_env()
                 h.set_split_k(s if s > 1 else 1)
                 t = timed()
                 print(json.dumps(dict(m=m, n=n, k=k, dtype=args.dtype, cfg=cfg, slices=h.last_split_k, presplit=h.last_presplit,
                                       us=round(t * 1e3, 2), tflops=round(2.0 * m * n * k / t / 1e9, 1))), flush=True)
         os.environ.pop("PBX_TC_CONFIG", None)
+        h.reload_env()
         h.set_split_k(0)
         del a, b, c
     h.close()

@@ -42,12 +42,13 @@ def multi():
     blas._gemm_multicast(h, "n", "n", m, n, k, 1.0, a, m, b, k, 0.0, ptrs, m, dt)
 
 
+os.environ["PBX_MULTICAST_PUSH"] = "0"
+h_nopush = SB_Handle(0)          # the switch is read into the handle when it is created
+os.environ.pop("PBX_MULTICAST_PUSH", None)
+
+
 def multi_nopush():
-    os.environ["PBX_MULTICAST_PUSH"] = "0"
-    try:
-        multi()
-    finally:
-        os.environ.pop("PBX_MULTICAST_PUSH", None)
+    blas._gemm_multicast(h_nopush, "n", "n", m, n, k, 1.0, a, m, b, k, 0.0, ptrs, m, dt)
 
 
 runs = {"plain": plain, "multicast_push": multi, "multicast_epilogue_stores": multi_nopush}
