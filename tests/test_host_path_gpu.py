@@ -81,3 +81,44 @@ def test_host_k_streamed_first_block(handle, tdt):
     for (ta, tb), beta, pad in itertools.product(TRANS, [0.0, 0.5], [0, 4]):
         _check(handle, tdt, ta, tb, 520, 2048 + 300, 2048 + 136, 1.5, beta, pad)
     _check(handle, tdt, "n", "n", 300, 4096 + 24, 9000, -0.5, 2.0, 4)
+
+
+def test_host_path_validates_before_it_copies(handle):
+    """pbx_gemm_host sizes its host <-> device copies from the strides, so pbx_gemm's validation (same order, same texts:
+    gemm_interface.hpp:144-165) runs BEFORE any buffer size is derived; batch == 0 is the same no-op as in pbx_gemm."""
+    m = n = k = 16
+    a = torch.ones(4 * m * k).pin_memory()
+    b = torch.ones(4 * k * n).pin_memory()
+    c = torch.full((4 * m * n,), 3.0).pin_memory()
+    kw = dict(stridea=m * k, strideb=k * n, stridec=m * n, batch_size=4)
+    for bad, text in ((dict(kw, stridec=-m * n), "invalid _stridec"), (dict(kw, stridec=m * n - 1), "invalid _stridec"),
+                      (dict(kw, stridea=-1), "invalid _stridea"), (dict(kw, strideb=-1), "invalid _strideb")):
+        with pytest.raises(ValueError, match=text):
+            blas.gemm_host(handle, "n", "n", m, n, k, 1.0, a, m, b, k, 0.0, c, m, **bad)
+    with pytest.raises(ValueError, match="invalid _TransA"):
+        blas.gemm_host(handle, "x", "n", m, n, k, 1.0, a, m, b, k, 0.0, c, m, **kw)
+    with pytest.raises(ValueError, match="invalid _TransB"):
+        blas.gemm_host(handle, "n", "y", m, n, k, 1.0, a, m, b, k, 0.0, c, m, **kw)
+    blas.gemm_host(handle, "n", "n", m, n, k, 1.0, a, m, b, k, 0.0, c, m, **dict(kw, batch_size=0))   # no-op
+    assert bool((c == 3.0).all()), "nothing may be written for batch == 0 or after a rejected call"
+
+
+def test_calls_leave_the_current_device_alone(handle):
+    """Every entry point works on the handle's device and restores the caller's current device (a single-process
+    multi-GPU torch program must not be switched to another GPU by a library call).  With one GPU the check is that
+    the current device is untouched; with two, a handle on device 1 is driven while device 0 is current."""
+    from portblas_b200 import SB_Handle
+    before = torch.cuda.current_device()
+    dev = 1 if torch.cuda.device_count() > 1 else 0
+    with torch.cuda.device(dev):
+        stream_ptr = torch.cuda.current_stream(dev).cuda_stream
+    h = SB_Handle(dev, stream_ptr)
+    assert torch.cuda.current_device() == before
+    x = torch.ones(64 * 64, device=f"cuda:{dev}")
+    y = torch.zeros(64 * 64, device=f"cuda:{dev}")
+    blas._gemm(h, "n", "n", 64, 64, 64, 1.0, x, 64, x, 64, 0.0, y, 64)
+    h.wait()
+    assert torch.cuda.current_device() == before
+    assert bool((y == 64.0).all())
+    h.close()
+    assert torch.cuda.current_device() == before
