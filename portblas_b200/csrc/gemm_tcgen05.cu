@@ -404,7 +404,7 @@ int pbx_launch_tcgen05(pbx_handle_t h, const PbxGemmCall& c, int slices) {
   p.batch = (int)c.batch; p.slices = slices;
   p.m_tiles = (int)((p.M + BM * cg - 1) / (BM * cg));
   p.n_tiles = (int)((p.N + bn - 1) / bn);
-  p.group_m = cg == 2 ? 8 : 16;
+  p.group_m = h->knobs.group_m > 0 ? h->knobs.group_m : (cg == 2 ? 8 : 16);
   p.kb_total = (int)((c.k + bk - 1) / bk);
   p.kb_per_slice = (p.kb_total + slices - 1) / slices;
   // fp32: the tensor core truncates when it adds into its fp32 accumulator, so an accumulation

@@ -92,6 +92,7 @@ int pbx_reload_env(pbx_handle_t h) {
   k.wait_hint_ns = (unsigned)geti("PBX_WAIT_HINT_NS", 0);
   k.tma_store = geti("PBX_TMA_STORE", 1);
   k.ilv_via_strided = geti("PBX_ILV_VIA_STRIDED", -1);
+  k.group_m = geti("PBX_GROUP_M", 0);
   h->knobs = k;
   h->dynamic_sched = geti("PBX_DYNAMIC_SCHED", 1) != 0;
   h->pdl = geti("PBX_PDL", 1) != 0;

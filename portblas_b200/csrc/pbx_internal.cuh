@@ -55,6 +55,7 @@ struct PbxKnobs {
   unsigned wait_hint_ns = 0;  // PBX_WAIT_HINT_NS: suspend-time hint of the long mbarrier waits (measured: no gain)
   int tma_store = 1;          // PBX_TMA_STORE=0: 16-bit C by direct stores
   int ilv_via_strided = -1;   // PBX_ILV_VIA_STRIDED=0/1: never / always re-lay interleaved batches out (-1: by shape)
+  int group_m = 0;            // PBX_GROUP_M: M tiles per raster group (0: 8 for CTA pairs, 16 for single CTAs)
 };
 
 struct pbx_handle_s {

@@ -43,6 +43,11 @@ VARIANTS = {
     "chunk64": ({}, {"PBX_TF32_CHUNK_KB": "64"}),      # exceed the fp32 error budget
     "chunk_inf": ({}, {"PBX_TF32_CHUNK_KB": "1000000"}),
     "presplit_off": ({}, {"PBX_TF32_PRESPLIT": "0"}),
+    "gm4": ({}, {"PBX_GROUP_M": "4"}),
+    "gm6": ({}, {"PBX_GROUP_M": "6"}),
+    "gm12": ({}, {"PBX_GROUP_M": "12"}),
+    "gm16": ({}, {"PBX_GROUP_M": "16"}),
+    "gm32": ({}, {"PBX_GROUP_M": "32"}),
     "hint1us": ({}, {"PBX_WAIT_HINT_NS": "1000"}),
     "hint20us": ({}, {"PBX_WAIT_HINT_NS": "20000"}),
     "hint1ms": ({}, {"PBX_WAIT_HINT_NS": "1000000"}),
