@@ -20,6 +20,8 @@
 
 #include <type_traits>
 
+#include <atomic>
+
 #include "pbx_internal.cuh"
 #include "tc_ptx.cuh"
 
@@ -277,10 +279,10 @@ __global__ void __launch_bounds__(DTHREADS, 1) gemm_dmma_kernel(DmmaParams p) {
 template <bool AK, bool BK_, int VEC>
 int launch_variant(pbx_handle_t h, const DmmaParams& p, dim3 grid) {
   auto kern = gemm_dmma_kernel<AK, BK_, VEC>;
-  static bool attr_set[16] = {};   // per device ordinal: the attribute is sticky, set it once
-  if (h->device >= 16 || !attr_set[h->device]) {
+  static std::atomic<uint32_t> attr_set{0};   // bit per device ordinal: the attribute is sticky, set it once
+  if (h->device >= 32 || !(attr_set.load(std::memory_order_acquire) & (1u << h->device))) {
     PBX_CUDA_CHECK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DMMA_SMEM_BYTES));
-    if (h->device < 16) attr_set[h->device] = true;
+    if (h->device < 32) attr_set.fetch_or(1u << h->device, std::memory_order_release);
   }
   kern<<<grid, DTHREADS, DMMA_SMEM_BYTES, h->stream>>>(p);
   h->launches++;
