@@ -92,7 +92,9 @@ typedef struct pbx_handle_s* pbx_handle_t;
  * (include/sb_handle/portblas_handle.h:46-200): one handle == one device +
  * one stream, caches the SM count (get_num_compute_units) and owns the
  * split-K workspace pool (Temp_Mem_Pool, include/sb_handle/temp_memory_pool.h:33-114).
- * Not thread-safe, like the reference (one handle per thread).              */
+ * Not thread-safe, like the reference (one handle per thread), and tied to ONE in-order stream at a time: the
+ * persistent kernel's tile counters and the pooled temporaries live in the handle, so two calls of the same handle
+ * must not run concurrently (change streams with pbx_set_stream only after pbx_synchronize).                    */
 int pbx_create(pbx_handle_t* out, int device_ordinal, void* cuda_stream /* cudaStream_t or NULL */);
 int pbx_destroy(pbx_handle_t h);
 int pbx_set_stream(pbx_handle_t h, void* cuda_stream);

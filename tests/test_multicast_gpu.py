@@ -54,6 +54,28 @@ def test_multicast_two_local_copies(handle, tin, tout):
         assert handle.last_kernel in ("tcgen05", "simt")
 
 
+@pytest.mark.parametrize("tin,tout", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16)])
+def test_multicast_copies_that_tma_cannot_address(handle, tin, tout):
+    """A leading dimension of C that is not a multiple of 16 bytes rules out the pusher's (and the 16-bit epilogue's)
+    tensor maps: the epilogue warps then store every tile to all copies themselves (round 1's form), three copies here."""
+    gen = torch.Generator(device="cuda").manual_seed(22)
+    for (m, n, k), (ta, tb), beta in itertools.product([(392, 264, 520), (520, 136, 264)], [("n", "n"), ("t", "t")], [0.0, 0.5]):
+        lda, ldb, ldc = (m if ta == "n" else k), (k if tb == "n" else n), m + 9
+        a = (torch.rand(lda * (k if ta == "n" else m), device="cuda", generator=gen) * 7 - 2).to(tin)
+        b = (torch.rand(ldb * (n if tb == "n" else k), device="cuda", generator=gen) * 7 - 2).to(tin)
+        c0 = (torch.rand(ldc * n, device="cuda", generator=gen) * 7 - 2).to(tout)
+        cs = [c0.clone(), torch.full_like(c0, 77.0), torch.full_like(c0, -5.0)]
+        blas._gemm_multicast(handle, ta, tb, m, n, k, 1.5, a, lda, b, ldb, beta, [c.data_ptr() for c in cs], ldc, tout)
+        handle.wait()
+        assert handle.last_kernel == "tcgen05"
+        want, bound = _ref(a, b, c0, ta, tb, m, n, k, lda, ldb, ldc, 1.5, beta)
+        g = [c.view(n, ldc).T for c in cs]
+        rel = float(((g[0][:m].double() - want).abs() / bound).max())
+        assert rel <= TOL[tout], f"{tin} {ta}{tb} {m}x{n}x{k} beta={beta}: {rel:.2e}"
+        assert torch.equal(g[0][:m], g[1][:m]) and torch.equal(g[0][:m], g[2][:m])
+        assert bool((g[1][m:] == 77.0).all()) and bool((g[2][m:] == -5.0).all()), "ld padding was written"
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
