@@ -43,6 +43,8 @@ VARIANTS = {
     "chunk64": ({}, {"PBX_TF32_CHUNK_KB": "64"}),      # exceed the fp32 error budget
     "chunk_inf": ({}, {"PBX_TF32_CHUNK_KB": "1000000"}),
     "presplit_off": ({}, {"PBX_TF32_PRESPLIT": "0"}),
+    "r01like": ({"PBX_DYNAMIC_SCHED": "0", "PBX_PDL": "0"}, {"PBX_F32_SPLIT16": "0"}),
+    "noswap": ({}, {"PBX_TC_SWAP": "0"}),
     "gm4": ({}, {"PBX_GROUP_M": "4"}),
     "gm6": ({}, {"PBX_GROUP_M": "6"}),
     "gm12": ({}, {"PBX_GROUP_M": "12"}),
