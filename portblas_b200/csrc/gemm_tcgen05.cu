@@ -254,7 +254,9 @@ TcPlan make_plan(pbx_handle_t h, const PbxGemmCall& c) {
   if (c.n_extra > 0) slices = 1;   // multicast epilogue: the tile is stored straight from TMEM, no split-K partials
   else if (h->forced_split_k > 1) slices = h->forced_split_k;
   else if (h->forced_split_k == 0 && tiles * 2 <= units && kb >= 16) {
-    slices = (2 * units) / tiles;
+    // one round of work items when the cost model is on (a second, partly filled round of very short tiles costs a
+    // whole pipeline fill: 64 x 147 x 13225 on 2 x 103 items 35 us, on one round 27 us); round 1's rule otherwise
+    slices = ((h->knobs.plan_model != 0 ? 1 : 2) * units) / tiles;
     if (slices > kb / 4) slices = kb / 4;
   }
   if (slices > kb) slices = kb;
