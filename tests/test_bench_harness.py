@@ -41,3 +41,41 @@ def test_fixture_rows_map_to_names():
     r = next(x for x in rows if x["api"] == "gemm")
     name = pb.bench_name("gemm", "float", [r["ta"], r["tb"], r["m"], r["k"], r["n"], r["alpha"], r["beta"]])
     assert name == f"BM_Gemm<float>/{r['ta']}/{r['tb']}/{r['m']}/{r['k']}/{r['n']}/usm"
+
+
+def _run_bench(extra_args, env_extra=None):
+    import os
+    import subprocess
+    env = dict(os.environ)
+    for key in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(key, None)
+    env.update(env_extra or {})
+    return subprocess.run([sys.executable, str(ROOT / "bench.py"), *extra_args], cwd=str(ROOT), env=env, capture_output=True,
+                          text=True, timeout=600)
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` needs no GPU: it times the reference's own CPU GEMM (oracle/_ref, else the port) on a
+    bounded sample and prints ONE JSON line in the driver's format."""
+    import json
+    r = _run_bench(["--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "0"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "gemm_tflops" and d["unit"] == "TFLOP/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 0
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None and d["dtype"] == "f32"
+    assert "16384" in d["config"]["workload"] and d["config"]["host_threads"] >= 1
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == dict(value=d["value"], unit="TFLOP/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
+    assert d["gpu_launches"] == 0
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    """Under torchrun (N > 1) rank 0 alone runs the reference arm; the other ranks exit 0 without work or output."""
+    r = _run_bench(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                   {"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
