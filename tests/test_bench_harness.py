@@ -79,3 +79,30 @@ def test_reference_arm_other_ranks_exit_quietly():
                    {"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
     assert r.returncode == 0, r.stderr[-2000:]
     assert not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_bench_algorithmic_work_and_roofline_choice():
+    """bench.py's per-launch algorithmic work is the reference's counter pair (blas3_state_counters.hpp:62-75: 2MNK flops,
+    (MK + KN + MN(1 or 2)) elements) and the roof is the one the arithmetic intensity selects."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+    w = bench.WORKLOADS["dgemm8192"]
+    fl, by = bench.algorithmic(w)
+    assert fl == 2.0 * 8192 ** 3 and by == 3 * 8192 * 8192 * 8
+    fl_tt, by_tt = bench.algorithmic(bench.WORKLOADS["dgemm8192_tt"])          # beta != 0: C is read as well
+    assert fl_tt == fl and by_tt == 4 * 8192 * 8192 * 8
+    w4 = bench.WORKLOADS["bf16gemm_batched"]                                    # cfg4: 85 flop/B -> HBM bound
+    fl4, by4 = bench.algorithmic(w4)
+    assert fl4 == 2.0 * 256 ** 3 * 4096 and by4 == 3 * 256 * 256 * 2 * 4096
+    r4 = bench.roofline_for(w4, 0.25, None)
+    assert r4["bound"] == "hbm" and r4["unit"] == "GB/s" and abs(r4["achieved"] - by4 / 0.25e-3 / 1e9) < 0.1
+    assert abs(r4["frac"] - r4["achieved"] / r4["peak"]) < 1e-3
+    pk = bench._peaks()
+    main = bench.WORKLOADS[bench.DEFAULT_WORKLOAD]
+    assert (main["m"], main["n"], main["k"], main["dt"]) == (16384, 16384, 16384, "f32")
+    r = bench.roofline_for(main, 30.0, 49.4e9, presplit=3)                      # tf32 + 2 x bf16: bf16 / 4
+    assert r["bound"] == "tensor" and abs(r["peak"] - pk["bf16"] / 4) < 0.06 and r["traffic"] == 49.4e9
+    assert abs(r["achieved"] - 2.0 * 16384 ** 3 / 30e-3 / 1e12) < 0.01
+    assert abs(bench.roofline_for(main, 30.0, None, presplit=0)["peak"] - pk["bf16"] / 6) < 0.06   # 3xTF32
+    assert abs(bench.roofline_for(main, 30.0, None, presplit=2)["peak"] - pk["bf16"] / 2) < 0.06   # single tf32
+    assert bench.roofline_for(w, 31.0, None)["peak"] == bench.NOMINAL_FP64_TFLOPS
