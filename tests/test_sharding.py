@@ -29,6 +29,31 @@ def test_split_range_covers_everything():
         assert pos == total
 
 
+def test_split_range_properties():
+    """pbx_shard_range over random problems: the parts tile [0, total) in rank order, every boundary but the end is a
+    multiple of `align`, and no two parts differ by more than one aligned unit (the balance bench.py's strong scaling
+    relies on); invalid arguments are rejected."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(0, 1 << 40), st.integers(1, 16), st.sampled_from([1, 2, 7, 128, 256, 1000]))
+    def check(total, world, align):
+        parts = [sharding.split_range(total, world, r, align) for r in range(world)]
+        pos = 0
+        for s, c in parts:
+            assert s == pos and c >= 0
+            pos += c
+            assert pos == total or pos % align == 0
+        assert pos == total
+        units = [-(-c // align) for _, c in parts]
+        assert max(units) - min(units) <= 1
+        assert sorted(units, reverse=True) == units          # earlier ranks take the remainder
+    check()
+    for bad in [(-1, 2, 0, 1), (10, 0, 0, 1), (10, 2, 2, 1), (10, 2, -1, 1), (10, 2, 0, 0)]:
+        with pytest.raises(ValueError):
+            sharding.split_range(*bad)
+
+
 def test_shard_offsets():
     sh = sharding.shard_mblock("n", 16384, 16384, 8, 3)
     assert (sh.row0, sh.rows, sh.a_offset, sh.c_offset) == (6144, 2048, 6144, 6144)
