@@ -79,3 +79,35 @@ def test_invalid_queries(pbx_lib):
     assert pbx_lib.pbx_plan_query(0, F32, 8, 8, 8, 1, *args) == 6
     assert pbx_lib.pbx_plan_query(148, _lib.F64, 8, 8, 8, 1, *args) == 6      # fp64 runs on the DMMA kernel
     assert pbx_lib.pbx_plan_query(148, F32, 0, 8, 8, 1, *args) == 6
+
+
+def test_plan_invariants_over_random_shapes(pbx_lib):
+    """Whatever the shape, the plan is one the kernels can run: a pair tile only where M (and N for 256-wide tiles) can
+    feed it, the operand swap exactly for skinny M, K slices that all own at least one K block (an empty slice would add
+    an uninitialised partial in the reduce), at least 4 K blocks per slice when the planner chose to split, and not more
+    work items than two rounds of the machine unless the tiles alone exceed that."""
+    from hypothesis import given, settings, strategies as st
+    dims = st.one_of(st.integers(1, 600), st.integers(1, 20000))
+
+    @settings(max_examples=600, deadline=None)
+    @given(st.sampled_from([F32, F16, BF16]), dims, dims, st.one_of(st.integers(1, 5000), st.integers(1, 1 << 20)),
+           st.sampled_from([1, 1, 1, 3, 32, 1000]), st.sampled_from([148, 132, 74]))
+    def check(dt, m, n, k, batch, sms):
+        cg, bn, slices, swapped = plan(pbx_lib, dt, m, n, k, batch, sms)
+        assert cg in (1, 2) and bn in (64, 128, 256) and slices >= 1
+        assert swapped == (m <= 64 and n > m)
+        if swapped:
+            assert (cg, bn) == (1, 64)
+        else:
+            assert bn != 64 and not (cg == 2 and m <= 128) and not (bn == 256 and (n <= 128 or cg == 1))
+        k_block = 32 if dt == F32 else 64
+        kb = -(-k // k_block)
+        assert slices <= kb
+        per = -(-kb // slices)
+        assert per * (slices - 1) < kb                       # no empty trailing slice
+        if slices > 1:
+            assert kb >= 16 and per >= 4
+            units = sms // cg
+            tiles = (-(-n // 128) if swapped else -(-m // (128 * cg)) * -(-n // bn)) * batch
+            assert tiles * slices <= 2 * units
+    check()
