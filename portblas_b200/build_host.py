@@ -67,10 +67,12 @@ def build_reference_unittests() -> list:
         return []
     shim = ROOT / "tests" / "cpp" / "shim"
     built = []
+    # up to date = newer than every source and header; libpbx_gemm.so is linked dynamically (rpath), so a rebuilt library
+    # with the same include/pbx_gemm.h needs no relink
     for name, defs in REF_UNITTESTS.items():
         exe = OUT / f"ref_unittest_{name}"
         srcs = [REF / "test" / "unittest" / "main.cpp", REF / "test" / "unittest" / "blas3" / f"{name}.cpp"]
-        newest = max(p.stat().st_mtime for p in [*srcs, *ROOT.glob("include/**/*.h*"), *shim.rglob("*.h"), HERE / "libpbx_gemm.so"])
+        newest = max(p.stat().st_mtime for p in [*srcs, *ROOT.glob("include/**/*.h*"), *shim.rglob("*.h")])
         if exe.exists() and exe.stat().st_mtime >= newest:
             built.append(exe)
             continue
@@ -119,7 +121,7 @@ def build_reference_joint_matrix_tests() -> list:
     def one(name: str) -> Path:
         exe = OUT / f"ref_unittest_joint_matrix_{name}"
         srcs = [REF / "test" / "unittest" / "main.cpp", jdir / f"{name}.cpp"]
-        newest = max(p.stat().st_mtime for p in [*srcs, *ROOT.glob("include/**/*.h*"), *shim.rglob("*.h"), HERE / "libpbx_gemm.so"])
+        newest = max(p.stat().st_mtime for p in [*srcs, *ROOT.glob("include/**/*.h*"), *shim.rglob("*.h")])
         if exe.exists() and exe.stat().st_mtime >= newest:
             return exe
         cmd = [CXX, "-std=c++17", "-O1", "-I", str(ROOT / "include"), "-I", "/usr/local/cuda/include", "-I", str(shim),
@@ -148,7 +150,7 @@ def build_reference_benchmarks() -> list:
     for name, defs in REF_BENCHMARKS.items():
         exe = OUT / f"ref_bench_{name}"
         srcs = [bdir / "main.cpp", bdir / "blas3" / f"{name}.cpp", shim / "bench_info_stub.cc"]
-        newest = max(p.stat().st_mtime for p in [*srcs, *ROOT.glob("include/**/*.h*"), *shim.rglob("*.h"), HERE / "libpbx_gemm.so"])
+        newest = max(p.stat().st_mtime for p in [*srcs, *ROOT.glob("include/**/*.h*"), *shim.rglob("*.h")])
         if exe.exists() and exe.stat().st_mtime >= newest:
             built.append(exe)
             continue
